@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE metric: footprint solves/s (and mode-levels/s) at 512x512x64 FP64.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is ONE footprint solve of BASELINE config 2 (512x512 grid, n=64 -> 105 z-levels, modes
+512x512, padded 1536x1536, unstable MOST profiles, FP64, level z_m).  N > 1 (torchrun, one rank
+per GPU): every rank runs its own K solves (independent solves shard with no data-path collective;
+weak scaling); time = max over ranks; value = N*K / time.
+
+  value     device-resident throughput: results stay in HBM, per-step CUDA events on the plan's
+            stream, L2 flushed (256 MiB memset) between steps.
+  e2e       same metric through the public Python API `steady_state_transport_solver` with host
+            numpy inputs/outputs (H2D of the staged profiles, D2H of conc+flx inside the timing).
+  roofline  the dominant kernel (fused march): algorithmic flops 86*M*S / measured
+            kernel time, against the FP64 pipe rate measured in this run by a DADD/DMUL (exact
+            mode) or DFMA (fma mode) micro-benchmark; the HBM view is given alongside.
+  cpu_baseline  the oracle port (C march with all host threads + scipy.fft) on the same config.
+
+`--impl reference` times that CPU port alone (the reference itself is pure Python + numba and is
+not available on the GPU box).
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "footprint_solves_per_s_512x512x64_fp64"
+UNIT = "solves/s"
+
+
+def config2():
+    from bldfm_b200.pbl_model import vertical_profiles
+
+    z, profs = vertical_profiles(64, 10.0, (-3.0, -4.0), ustar=0.4, mol=-50.0)
+    return dict(srf_flx=np.zeros((512, 512)), z=z, profiles=profs, domain=(4000.0, 4000.0), levels=64,
+                modes=(512, 512), meas_pt=(2000.0, 2000.0), footprint=True, precision="double")
+
+
+WORKLOAD = ("BASELINE config 2: single-tower footprint 512x512, n=64 (105 levels, 104 march steps), "
+            "modes 512x512, halo=4000 m (padded 1536x1536), unstable MOST (ustar=0.4, L=-50 m, "
+            "wind (-3,-4)), level z_m, FP64")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_leg(kw, steps, warmup, nthreads):
+    """Time the oracle port (CPU) on config 2: returns (solves/s, ms_per_step)."""
+    from oracle import bldfm_oracle as O
+
+    O.build()
+    for _ in range(warmup):
+        O.solve(nthreads=nthreads, **kw)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.solve(nthreads=nthreads, **kw)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps * 1e3
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import bldfm_oracle as O
+
+    O.build()
+    kw = config2()
+    cores = O.max_threads()
+    steps = max(1, min(args.steps, 12))
+    warm = max(1, min(args.warmup, 2))
+    sps, ms = cpu_reference_leg(kw, steps, warm, cores)
+    g = O.geometry(kw["srf_flx"].shape, kw["domain"], kw["modes"], None)
+    mode_levels = (g["nlx"] * g["nly"] - 1) * (len(kw["z"]) - 1)
+    sample = f"{steps} full config-2 solves (oracle port: pthread C march x{cores} + scipy.fft workers={cores})"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD},
+        "mode_levels_per_s": sps * mode_levels,
+        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="problems per launch for the extra batched figure")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    args.warmup = max(args.warmup, 3)
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    import bldfm_b200
+    from bldfm_b200 import _lib
+
+    if not torch.cuda.is_available() or _lib.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device (bldfm_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    bldfm_b200.config.DEVICE = local
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    L = _lib.lib()
+    kw = config2()
+    geom = _lib.geometry(kw["srf_flx"].shape, kw["domain"], kw["modes"], None)
+    M = geom.nlx * geom.nly - 1
+    S = len(kw["z"]) - 1
+    mode_levels = M * S
+    fma_mode = bldfm_b200.config.MARCH_MODE == "fma"
+    flags = _lib.FOOTPRINT | _lib.DOUBLE | _lib.OUT_ON_DEVICE | _lib.ASYNC | (_lib.MARCH_FMA if fma_mode else 0)
+    if bldfm_b200.config.FFT_LIBRARY:
+        flags |= _lib.FFT_LIBRARY
+
+    plan = bldfm_b200.get_fft_manager().plan(geom, local)
+    stream = torch.cuda.ExternalStream(L.bldfm_plan_stream(plan), device=local)
+    prob, keep = _lib.make_problem(kw["z"], kw["profiles"], kw["meas_pt"], 0.0)
+    lv = np.array([kw["levels"]], dtype=np.int64)
+    lvp = lv.ctypes.data_as(C.POINTER(C.c_int64))
+    out_c = torch.empty((512, 512), dtype=torch.float64, device=f"cuda:{local}")
+    out_f = torch.empty_like(out_c)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
+
+    def solve_dev():
+        _lib.check(L.bldfm_solve(plan, C.byref(prob), lvp, 1, None, flags, out_c.data_ptr(), out_f.data_ptr()))
+
+    def flush_l2():
+        with torch.cuda.stream(stream):
+            flush.zero_()
+
+    # ---- FP64 pipe peak measured in this run (roofline denominator)
+    peak_ops = C.c_double(0.0)
+    _lib.check(L.bldfm_fp64_peak(local, 1 if fma_mode else 0, 20000, C.byref(peak_ops)))
+    peak_fma = C.c_double(0.0)
+    _lib.check(L.bldfm_fp64_peak(local, 1, 20000, C.byref(peak_fma)))
+
+    # ---- device-resident leg
+    for _ in range(args.warmup):
+        solve_dev()
+    barrier()
+    launches0 = int(L.bldfm_plan_launch_count(plan))
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(local) as clocks:
+        barrier()
+        for a, b in ev:
+            flush_l2()
+            a.record(stream)
+            solve_dev()
+            b.record(stream)
+        barrier()
+    launches = int(L.bldfm_plan_launch_count(plan)) - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+
+    # ---- kernel timing for the roofline (per-stage events inside the library)
+    L.bldfm_plan_set_profiling(plan, 1)
+    tm = _lib.Timings()
+    march_ms = inv_ms = 0.0
+    nprof = min(args.steps, 20)
+    for _ in range(nprof):
+        flush_l2()
+        solve_dev()
+        _lib.check(L.bldfm_plan_last_timings(plan, C.byref(tm)))
+        march_ms += tm.march_ms
+        inv_ms += tm.inverse_ms
+    march_ms /= nprof
+    inv_ms /= nprof
+    L.bldfm_plan_set_profiling(plan, 0)
+
+    # ---- end-to-end leg through the public API (host in, host out)
+    for _ in range(args.warmup):
+        bldfm_b200.steady_state_transport_solver(**kw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        grid, conc, flx = bldfm_b200.steady_state_transport_solver(**kw)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    # ---- batched figure (B distinct met conditions per launch), device-resident
+    B = args.batch
+    from bldfm_b200.pbl_model import vertical_profiles
+    probs, keeps = [], []
+    for b in range(B):
+        zb, pb = vertical_profiles(64, 10.0, (-3.0 - 0.05 * b, -4.0 + 0.03 * b), ustar=0.4, mol=-50.0 - b)
+        if len(zb) != len(kw["z"]):
+            zb, pb = kw["z"], kw["profiles"]
+        p_, k_ = _lib.make_problem(zb, pb, kw["meas_pt"], 0.0)
+        probs.append(p_)
+        keeps.append(k_)
+    parr = (_lib.Problem * B)(*probs)
+    bout_c = torch.empty((B, 512, 512), dtype=torch.float64, device=f"cuda:{local}")
+    bout_f = torch.empty_like(bout_c)
+
+    def solve_batch():
+        _lib.check(L.bldfm_solve_batched(plan, B, parr, lvp, 1, None, flags, bout_c.data_ptr(), bout_f.data_ptr()))
+
+    for _ in range(3):
+        solve_batch()
+    torch.cuda.synchronize()
+    nb = max(3, args.steps // 4)
+    bev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nb)]
+    for a, b in bev:
+        flush_l2()
+        a.record(stream)
+        solve_batch()
+        b.record(stream)
+    torch.cuda.synchronize()
+    batch_ms = sum(a.elapsed_time(b) for a, b in bev) / nb
+
+    # ---- reduce over ranks (max time)
+    t = torch.tensor([dev_ms, e2e_s * 1e3, march_ms, batch_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, march_ms_max, batch_ms = (float(x) for x in t.tolist())
+
+    if rank == 0:
+        value = world * args.steps / (dev_ms * 1e-3)
+        e2e = world * args.steps / (e2e_ms * 1e-3)
+        flops = 86.0 * M * S
+        achieved = flops / (march_ms * 1e-3) * 1e-12
+        peak = (peak_ops.value * (2.0 if fma_mode else 1.0)) * 1e-3        # TFLOP/s
+        alg_bytes = 2 * geom.nlx * geom.nly * 16 + S * 128
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "march_mode": bldfm_b200.config.MARCH_MODE,
+                       "fft": "cufft" if bldfm_b200.config.FFT_LIBRARY else "auto",
+                       "l2": "flushed with a 256 MiB memset between timed steps"},
+            "mode_levels_per_s": value * mode_levels,
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": int(S * 128 + 64 + 24 + (S + 1) * 4),
+                    "d2h_bytes_per_step": int(2 * 512 * 512 * 8),
+                    "api": "bldfm_b200.steady_state_transport_solver (numpy in/out)"},
+            "gpu_launches": launches,
+            "clocks": clocks.summary(),
+            "roofline": {
+                "kernel": "k_march (fused K4-K8)", "bound": "fp64", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                "flops_per_launch": flops, "kernel_ms": march_ms,
+                "peak_source": ("measured in this run: bldfm_fp64_peak "
+                                + ("DFMA x2" if fma_mode else "DADD/DMUL (non-fused ops, exact mode)")),
+                "peak_dfma_tflops": peak_fma.value * 2e-3,
+                "hbm_view": {"algorithmic_bytes": alg_bytes,
+                             "achieved_gbs": alg_bytes / (march_ms * 1e-3) * 1e-9},
+                "share_of_step": march_ms / (dev_ms / args.steps),
+                "inverse_ms": inv_ms,
+            },
+            "batched": {"batch": B, "ms_per_batch": batch_ms, "solves_per_s": world * B / (batch_ms * 1e-3),
+                        "mode_levels_per_s": world * B / (batch_ms * 1e-3) * mode_levels},
+        }
+        if not args.no_cpu:
+            from oracle import bldfm_oracle as O
+            cores = O.max_threads()
+            sps, ms = cpu_reference_leg({**kw}, 4, 1, cores)
+            line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "4 full config-2 solves (oracle port: pthread C march + scipy.fft, all host threads)",
+                                    "ms_per_step": ms}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

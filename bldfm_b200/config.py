@@ -1,0 +1,24 @@
+"""Runtime settings (mirror of the reference's src/bldfm/config.py:43-49 runtime globals).
+
+NUM_THREADS / MAX_WORKERS are accepted for drop-in compatibility; the CUDA path ignores them
+(the march is one GPU thread per Fourier mode, the drivers batch instead of forking).
+"""
+
+import os
+
+# --- reference runtime globals (config.py:43-49)
+NUM_THREADS = 1
+MAX_WORKERS = 1
+USE_CACHE = False
+
+# --- bldfm_b200 additions
+# CUDA device used by this process (one process per GPU; torchrun sets LOCAL_RANK).
+DEVICE = int(os.environ.get("BLDFM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+# "exact": march bit-mirrors the reference's operation order (default).
+# "fma":   FMA-contracted march, ~1.8x fewer FP64 instructions, differs at the self-noise level.
+MARCH_MODE = os.environ.get("BLDFM_B200_MARCH", "exact")
+# True: grid arrays (X, Y, Z) are materialised like the reference's np.meshgrid (solver.py:296).
+# False: zero-copy read-only broadcast views with identical values and shapes.
+GRID_COPY = os.environ.get("BLDFM_B200_GRID_COPY", "0") == "1"
+# Force the library (cuFFT) transform path instead of the pruned in-house kernels.
+FFT_LIBRARY = os.environ.get("BLDFM_B200_FFT_LIBRARY", "0") == "1"

@@ -1,0 +1,956 @@
+// api.cu -- plan management and the C ABI of libbldfm_b200 (see include/bldfm_b200.h).
+//
+// Host-side orchestration of the hot path: K1-K3 (source spectrum), K4-K8 (fused march kernel),
+// K9-K11 (back-transform + crop).  No CPU compute fallback exists: every entry point that computes
+// fails with BLDFM_ERR_CUDA when no device is usable.
+#include "../../include/bldfm_b200.h"
+
+#include <cufft.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "march.cuh"
+#include "transform.cuh"
+#include "fft.cuh"
+
+using namespace bldfm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                       \
+    do {                                                                                     \
+        cudaError_t e__ = (expr);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return fail(BLDFM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+#define CUFFT_TRY(expr)                                                                      \
+    do {                                                                                     \
+        cufftResult r__ = (expr);                                                            \
+        if (r__ != CUFFT_SUCCESS)                                                            \
+            return fail(BLDFM_ERR_CUFFT, std::string(#expr) + ": cufft error " + std::to_string((int)r__)); \
+    } while (0)
+
+#define TRY(expr)                    \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ != BLDFM_OK) return rc__; \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    // grow-only; returns BLDFM_OK; *grew tells the caller the contents are undefined (fresh)
+    int ensure(size_t bytes, bool* grew = nullptr)
+    {
+        if (grew) *grew = false;
+        if (bytes <= cap) return BLDFM_OK;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        size_t want = bytes;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(BLDFM_ERR_ALLOC, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+        }
+        cap = want;
+        if (grew) *grew = true;
+        return BLDFM_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+    }
+};
+
+struct Staging {
+    void* host = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    bool in_flight = false;
+};
+
+constexpr int kStagingSlots = 4;
+
+}  // namespace
+
+struct bldfm_plan {
+    int device = 0;
+    bldfm_geometry g{};
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    size_t smem_optin = 0;
+
+    DevBuf tables;      // lx[nlx] ly[nly]
+    DevBuf params;      // coef | groups | towers | row_of   (per solve)
+    DevBuf spec_p, spec_q;   // compact spectra [slot][row][nly][nlx]
+    DevBuf pad_in, pad_out;  // library path: padded spectra chunk
+    size_t pad_state_elem = 0, pad_state_fields = 0;   // what the static zeros of pad_in match
+    DevBuf src_in, src_pad;  // non-footprint: device copy of srf_flx, padded complex / spectrum
+    DevBuf fft_work;         // pruned path: intermediate [field][nly][nx]
+    DevBuf out_c, out_f;     // device outputs when the caller wants host results
+    Staging staging[kStagingSlots];
+    int staging_next = 0;
+    std::map<uint64_t, cufftHandle> fft_plans;
+    int64_t launches = 0;
+    bool profiling = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_recorded = false;
+    size_t pad_budget = (size_t)1 << 30;   // bytes per padded chunk buffer (library path)
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---- host arithmetic (compiled with -ffp-contract=off; mirrors the reference's order) ------------
+
+void fill_coefs(const bldfm_problem& pb, LevelCoef* lc)
+{
+    const int S = pb.nz - 1;
+    for (int i = 0; i < S; ++i) {
+        const double kinv = 1.0 / pb.Kz[i];                  // solver.py:358
+        const double h = pb.z[i + 1] - pb.z[i];              // solver.py:341
+        LevelCoef& c = lc[i];
+        c.Kx = pb.Kx[i]; c.Ky = pb.Ky[i]; c.u = pb.u[i]; c.v = pb.v[i];
+        c.s = 0.5 * kinv;
+        c.h = h;
+        c.h2 = h * h;
+        c.h3 = (h * h) * h;
+        c.s6 = (1.0 / 6.0) * (kinv * kinv);
+        c.s61 = (1.0 / 6.0) * kinv;
+        c.c0 = (-kinv) * h;
+        c.w = 0.5 / pb.Kz[i] + 0.5 / pb.Kz[i + 1];           // solver.py:248
+        c.sh2 = c.s * c.h2;
+        c.s6h3 = c.s6 * c.h3;
+        c.s61h3 = c.s61 * c.h3;
+        c.pad = 0.0;
+    }
+}
+
+void fill_group(const bldfm_problem& pb, GroupDesc& gd)
+{
+    const int nz = pb.nz;
+    gd.S = nz - 1;
+    gd.kz_top = pb.Kz[nz - 1];
+    gd.kinv_top = 1.0 / pb.Kz[nz - 1];                       // solver.py:164
+    gd.kxk = pb.Kx[nz - 1] * gd.kinv_top;                    // :165
+    gd.kyk = pb.Ky[nz - 1] * gd.kinv_top;                    // :166
+    gd.c1 = pb.u[nz - 1] * gd.kinv_top;                      // :172
+    gd.c2 = pb.v[nz - 1] * gd.kinv_top;                      // :173
+    gd.p000 = pb.srf_bg_conc;
+    gd.h_analytic = 0.0;
+    gd.pad = 0;
+}
+
+uint64_t fnv1a(const void* data, size_t n, uint64_t h)
+{
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+uint64_t problem_hash(const bldfm_problem& pb)
+{
+    uint64_t h = 1469598103934665603ull;
+    h = fnv1a(&pb.nz, sizeof(pb.nz), h);
+    const size_t nb = sizeof(double) * (size_t)pb.nz;
+    h = fnv1a(pb.z, nb, h); h = fnv1a(pb.u, nb, h); h = fnv1a(pb.v, nb, h);
+    h = fnv1a(pb.Kx, nb, h); h = fnv1a(pb.Ky, nb, h); h = fnv1a(pb.Kz, nb, h);
+    h = fnv1a(&pb.srf_bg_conc, sizeof(double), h);
+    return h;
+}
+
+bool same_march(const bldfm_problem& a, const bldfm_problem& b)
+{
+    if (a.nz != b.nz) return false;
+    const size_t nb = sizeof(double) * (size_t)a.nz;
+    return !memcmp(a.z, b.z, nb) && !memcmp(a.u, b.u, nb) && !memcmp(a.v, b.v, nb) &&
+           !memcmp(a.Kx, b.Kx, nb) && !memcmp(a.Ky, b.Ky, nb) && !memcmp(a.Kz, b.Kz, nb) &&
+           !memcmp(&a.srf_bg_conc, &b.srf_bg_conc, sizeof(double));
+}
+
+int grid_for(int64_t n, int threads, int num_sms)
+{
+    int64_t blocks = (n + threads - 1) / threads;
+    const int64_t cap = (int64_t)num_sms * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+int acquire_staging(bldfm_plan* pl, size_t bytes, Staging** out)
+{
+    Staging& s = pl->staging[pl->staging_next];
+    pl->staging_next = (pl->staging_next + 1) % kStagingSlots;
+    if (s.in_flight) { CUDA_TRY(cudaEventSynchronize(s.done)); s.in_flight = false; }
+    if (!s.done) CUDA_TRY(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    if (bytes > s.cap) {
+        if (s.host) cudaFreeHost(s.host);
+        s.host = nullptr; s.cap = 0;
+        size_t want = std::max(bytes, (size_t)1 << 16);
+        CUDA_TRY(cudaMallocHost(&s.host, want));
+        s.cap = want;
+    }
+    *out = &s;
+    return BLDFM_OK;
+}
+
+int get_fft_plan(bldfm_plan* pl, int nfy, int nfx, cufftType type, int batch, cufftHandle* out)
+{
+    const uint64_t key = ((uint64_t)(type == CUFFT_Z2Z ? 1 : 0) << 62) | ((uint64_t)batch << 40) |
+                         ((uint64_t)nfy << 20) | (uint64_t)nfx;
+    auto it = pl->fft_plans.find(key);
+    if (it != pl->fft_plans.end()) { *out = it->second; return BLDFM_OK; }
+    cufftHandle h;
+    int n[2] = {nfy, nfx};
+    CUFFT_TRY(cufftPlanMany(&h, 2, n, nullptr, 1, nfy * nfx, nullptr, 1, nfy * nfx, type, batch));
+    CUFFT_TRY(cufftSetStream(h, pl->stream));
+    pl->fft_plans[key] = h;
+    *out = h;
+    return BLDFM_OK;
+}
+
+struct LevelPlan {
+    std::vector<int32_t> row_of;   // [nz_max]
+    int visited = 0;
+    int snap_level = -1;
+    int last_level = -1;
+};
+
+// mirrors the `i in levels` / lvl counter logic of solver.py:348-355, 370-372
+int build_levels(const int64_t* levels, int nlv, int nz_min, int nz_max, LevelPlan& lp)
+{
+    for (int k = 0; k < nlv; ++k)
+        if (levels[k] >= nz_min || levels[k] < -(int64_t)nz_min)
+            return fail(BLDFM_ERR_LEVEL_RANGE, "index " + std::to_string((long long)levels[k]) +
+                                                   " is out of bounds for axis 0 with size " +
+                                                   std::to_string(nz_min));
+    lp.row_of.assign((size_t)nz_max, -1);
+    int row = 0;
+    for (int i = 0; i < nz_min; ++i) {
+        bool hit = false;
+        for (int k = 0; k < nlv; ++k) if (levels[k] == i) { hit = true; break; }
+        if (hit) {
+            lp.row_of[(size_t)i] = row++;
+            if (lp.snap_level < 0) lp.snap_level = i;
+            lp.last_level = i;
+        }
+    }
+    lp.visited = row;
+    return BLDFM_OK;
+}
+
+// ---- the solve pipeline ------------------------------------------------------------------------
+
+struct SolveOut {
+    void* conc = nullptr;
+    void* flx = nullptr;
+    double* tfftp = nullptr;   // spectral export (host)
+    double* tfftq = nullptr;
+};
+
+int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int64_t* levels,
+               int nlv, const double* srf_flx, int flags, const SolveOut& out)
+{
+    if (!pl) return fail(BLDFM_ERR_INVALID, "plan is NULL");
+    if (nprob < 1 || !probs) return fail(BLDFM_ERR_INVALID, "no problems given");
+    if (nlv < 1 || !levels) return fail(BLDFM_ERR_INVALID, "levels must hold at least one entry");
+    const bldfm_geometry& g = pl->g;
+    const bool footprint = flags & BLDFM_FOOTPRINT;
+    const bool analytic = flags & BLDFM_ANALYTIC;
+    const bool dbl = flags & BLDFM_DOUBLE;
+    const bool fma_mode = flags & BLDFM_MARCH_FMA;
+    const bool out_dev = flags & BLDFM_OUT_ON_DEVICE;
+    const bool spectral = out.tfftp != nullptr;
+    if (!footprint && !srf_flx) return fail(BLDFM_ERR_INVALID, "srf_flx is NULL in non-footprint mode");
+    if (!footprint && (g.nfx != g.nxe || g.nfy != g.nye))
+        return fail(BLDFM_ERR_ODD_PAD, "padded grid size minus modes must be even.");
+    if (analytic && nlv != 1)
+        return fail(BLDFM_ERR_ANALYTIC_LEVELS, "analytic=True supports a single output level.");
+
+    DeviceGuard guard(pl->device);
+    if (!guard.ok) return fail(BLDFM_ERR_CUDA, "cudaSetDevice failed");
+
+    int nz_min = probs[0].nz, nz_max = probs[0].nz;
+    for (int b = 0; b < nprob; ++b) {
+        const bldfm_problem& pb = probs[b];
+        if (pb.nz < 2 || !pb.z || !pb.u || !pb.v || !pb.Kx || !pb.Ky || !pb.Kz)
+            return fail(BLDFM_ERR_INVALID, "problem " + std::to_string(b) + ": need nz >= 2 and all profiles");
+        nz_min = std::min(nz_min, (int)pb.nz);
+        nz_max = std::max(nz_max, (int)pb.nz);
+    }
+    LevelPlan lp;
+    TRY(build_levels(levels, nlv, nz_min, nz_max, lp));
+
+    // ---- group problems that share a march
+    std::vector<int> group_of((size_t)nprob);
+    std::vector<int> rep;   // representative problem per group
+    {
+        std::multimap<uint64_t, int> seen;
+        for (int b = 0; b < nprob; ++b) {
+            const uint64_t h = nprob > 1 ? problem_hash(probs[b]) : 0;
+            int gidx = -1;
+            auto range = seen.equal_range(h);
+            for (auto it = range.first; it != range.second; ++it)
+                if (same_march(probs[rep[(size_t)it->second]], probs[b])) { gidx = it->second; break; }
+            if (gidx < 0) {
+                gidx = (int)rep.size();
+                rep.push_back(b);
+                seen.emplace(h, gidx);
+            }
+            group_of[(size_t)b] = gidx;
+        }
+    }
+    const int ngroups = (int)rep.size();
+    const int coef_stride = nz_max - 1;
+
+    // ---- shifts and output dtype
+    std::vector<TowerDesc> towers((size_t)nprob);
+    int n_shift = 0;
+    {
+        std::vector<int> count((size_t)ngroups, 0), begin((size_t)ngroups, 0), fill((size_t)ngroups, 0);
+        for (int b = 0; b < nprob; ++b) count[(size_t)group_of[(size_t)b]]++;
+        for (int gi = 1; gi < ngroups; ++gi) begin[(size_t)gi] = begin[(size_t)gi - 1] + count[(size_t)gi - 1];
+        for (int b = 0; b < nprob; ++b) {
+            const bldfm_problem& pb = probs[b];
+            TowerDesc td{};
+            td.slot = b;
+            if (footprint) {
+                td.shift = 1;
+                td.sx = pb.xm + g.halo;                               // solver.py:255
+                td.sy = pb.ym + g.halo;
+            } else if (pb.xm * pb.xm + pb.ym * pb.ym > 0.0) {         // solver.py:259
+                td.shift = 1;
+                td.sx = pb.xm - g.xmax / 2;                           // solver.py:260
+                td.sy = pb.ym - g.ymax / 2;
+            } else {
+                td.shift = 0; td.sx = 0.0; td.sy = 0.0;
+            }
+            n_shift += td.shift;
+            const int gi = group_of[(size_t)b];
+            towers[(size_t)(begin[(size_t)gi] + fill[(size_t)gi]++)] = td;
+        }
+        // stash begin/count for the group descriptors below
+        group_of.clear();
+        group_of.insert(group_of.end(), begin.begin(), begin.end());
+        group_of.insert(group_of.end(), count.begin(), count.end());
+    }
+    if (!dbl && n_shift != 0 && n_shift != nprob)
+        return fail(BLDFM_ERR_INVALID, "precision='single' batch mixes shifted and unshifted meas_pt (float32/float64 outputs)");
+    const bool out_f32 = !dbl && n_shift == 0;
+    const bool spec_f32 = out_f32 && !spectral;
+    const size_t celem = spec_f32 ? sizeof(float2) : sizeof(double2);
+    const size_t relem = out_f32 ? sizeof(float) : sizeof(double);
+
+    // ---- stage per-solve parameters: coef | groups | towers | row_of
+    const size_t off_coef = 0;
+    const size_t sz_coef = (size_t)ngroups * coef_stride * sizeof(LevelCoef);
+    const size_t off_groups = off_coef + sz_coef;
+    const size_t sz_groups = (size_t)ngroups * sizeof(GroupDesc);
+    const size_t off_towers = off_groups + sz_groups;
+    const size_t sz_towers = (size_t)nprob * sizeof(TowerDesc);
+    const size_t off_rows = off_towers + sz_towers;
+    const size_t sz_rows = (size_t)nz_max * sizeof(int32_t);
+    const size_t sz_params = off_rows + sz_rows;
+
+    Staging* st = nullptr;
+    TRY(acquire_staging(pl, sz_params, &st));
+    {
+        char* base = static_cast<char*>(st->host);
+        LevelCoef* lc = reinterpret_cast<LevelCoef*>(base + off_coef);
+        GroupDesc* gds = reinterpret_cast<GroupDesc*>(base + off_groups);
+        for (int gi = 0; gi < ngroups; ++gi) {
+            const bldfm_problem& pb = probs[rep[(size_t)gi]];
+            LevelCoef* dst = lc + (size_t)gi * coef_stride;
+            fill_coefs(pb, dst);
+            if (pb.nz - 1 < coef_stride)
+                memset(dst + (pb.nz - 1), 0, sizeof(LevelCoef) * (size_t)(coef_stride - (pb.nz - 1)));
+            fill_group(pb, gds[gi]);
+            gds[gi].tow_begin = group_of[(size_t)gi];
+            gds[gi].tow_count = group_of[(size_t)ngroups + gi];
+            if (analytic) {
+                int64_t l = levels[0];
+                if (l < 0) l += pb.nz;
+                gds[gi].h_analytic = pb.z[l] - pb.z[0];           // solver.py:197
+            }
+        }
+        memcpy(base + off_towers, towers.data(), sz_towers);
+        memcpy(base + off_rows, lp.row_of.data(), sz_rows);
+    }
+    TRY(pl->params.ensure(sz_params));
+    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev[0], pl->stream));
+    CUDA_TRY(cudaMemcpyAsync(pl->params.p, st->host, sz_params, cudaMemcpyHostToDevice, pl->stream));
+    CUDA_TRY(cudaEventRecord(st->done, pl->stream));
+    st->in_flight = true;
+
+    // ---- K1-K3: spectrum of the padded source (non-footprint)
+    const double2* d_src_spec = nullptr;
+    if (!footprint) {
+        const double* d_q0 = srf_flx;
+        if (!(flags & BLDFM_SRC_ON_DEVICE)) {
+            TRY(pl->src_in.ensure(sizeof(double) * (size_t)g.nx * g.ny));
+            CUDA_TRY(cudaMemcpyAsync(pl->src_in.p, srf_flx, sizeof(double) * (size_t)g.nx * g.ny,
+                                     cudaMemcpyHostToDevice, pl->stream));
+            d_q0 = static_cast<const double*>(pl->src_in.p);
+        }
+        TRY(pl->src_pad.ensure(sizeof(double2) * (size_t)g.nxe * g.nye));
+        double2* d_pad = static_cast<double2*>(pl->src_pad.p);
+        k_pad_source<<<grid_for((int64_t)g.nxe * g.nye, 256, pl->num_sms), 256, 0, pl->stream>>>(
+            d_q0, d_pad, g.nx, g.ny, g.px, g.py, g.nxe, g.nye);
+        pl->launches++;
+        cufftHandle h;
+        TRY(get_fft_plan(pl, g.nye, g.nxe, CUFFT_Z2Z, 1, &h));
+        CUFFT_TRY(cufftExecZ2Z(h, reinterpret_cast<cufftDoubleComplex*>(d_pad),
+                               reinterpret_cast<cufftDoubleComplex*>(d_pad), CUFFT_FORWARD));
+        d_src_spec = d_pad;
+    }
+    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev[1], pl->stream));
+
+    // ---- K4-K8: fused march -> compact spectra
+    const int64_t nmodes = (int64_t)g.nlx * g.nly;
+    const int64_t nfields = (int64_t)nprob * nlv;
+    TRY(pl->spec_p.ensure((size_t)nfields * nmodes * celem));
+    TRY(pl->spec_q.ensure((size_t)nfields * nmodes * celem));
+    {
+        char* dbase = static_cast<char*>(pl->params.p);
+        MarchArgs a{};
+        a.nlx = g.nlx; a.nly = g.nly; a.nlv = nlv;
+        a.coef_stride = coef_stride; a.nrow_of = nz_max;
+        a.snap_level = lp.snap_level; a.last_level = lp.last_level;
+        a.single = dbl ? 0 : 1;
+        a.out_f32 = spec_f32 ? 1 : 0;
+        a.footprint = footprint ? 1 : 0;
+        a.src_pitch = g.nxe; a.src_nfx = g.nxe; a.src_nfy = g.nye;
+        a.q0_const = 1.0 / g.nxe / g.nye;                           // solver.py:134
+        a.src_scale = 1.0 / ((double)g.nxe * (double)g.nye);        // norm="forward"
+        a.src_spec = d_src_spec;
+        a.coef = reinterpret_cast<const LevelCoef*>(dbase + off_coef);
+        a.groups = reinterpret_cast<const GroupDesc*>(dbase + off_groups);
+        a.towers = reinterpret_cast<const TowerDesc*>(dbase + off_towers);
+        a.row_of = reinterpret_cast<const int32_t*>(dbase + off_rows);
+        a.lx = static_cast<const double*>(pl->tables.p);
+        a.ly = a.lx + g.nlx;
+        a.outp = pl->spec_p.p; a.outq = pl->spec_q.p;
+        a.slot_stride = (int64_t)nlv * nmodes;
+
+        const dim3 grid((unsigned)((nmodes + kMarchThreads - 1) / kMarchThreads), (unsigned)ngroups);
+        const size_t smem = (size_t)coef_stride * sizeof(LevelCoef) + (size_t)nz_max * sizeof(int32_t);
+        if (smem > pl->smem_optin)
+            return fail(BLDFM_ERR_INVALID, "nz too large for the shared-memory coefficient table (" +
+                                               std::to_string(nz_max) + " levels)");
+        if (analytic) {
+            k_analytic<<<grid, kMarchThreads, 0, pl->stream>>>(a);
+        } else {
+            const bool multi = lp.visited > 1;
+#define LAUNCH_MARCH(F, M)                                                                          \
+    do {                                                                                            \
+        CUDA_TRY(cudaFuncSetAttribute(k_march<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                      (int)pl->smem_optin));                                        \
+        k_march<F, M><<<grid, kMarchThreads, smem, pl->stream>>>(a);                                \
+    } while (0)
+            if (fma_mode) { if (multi) LAUNCH_MARCH(true, true); else LAUNCH_MARCH(true, false); }
+            else          { if (multi) LAUNCH_MARCH(false, true); else LAUNCH_MARCH(false, false); }
+#undef LAUNCH_MARCH
+        }
+        CUDA_TRY(cudaGetLastError());
+        pl->launches++;
+    }
+    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev[2], pl->stream));
+
+    if (spectral) {
+        // parity export of tfftp/tfftq before solver.py:265
+        const size_t nb = (size_t)nfields * nmodes * sizeof(double2);
+        CUDA_TRY(cudaMemcpyAsync(out.tfftp, pl->spec_p.p, nb, cudaMemcpyDeviceToHost, pl->stream));
+        CUDA_TRY(cudaMemcpyAsync(out.tfftq, pl->spec_q.p, nb, cudaMemcpyDeviceToHost, pl->stream));
+        CUDA_TRY(cudaStreamSynchronize(pl->stream));
+        return BLDFM_OK;
+    }
+
+    // ---- K9-K11: back-transform + crop
+    const int64_t out_per_field = (int64_t)g.nx * g.ny;
+    void* d_conc = out.conc;
+    void* d_flx = out.flx;
+    if (!out_dev) {
+        TRY(pl->out_c.ensure((size_t)nfields * out_per_field * relem));
+        TRY(pl->out_f.ensure((size_t)nfields * out_per_field * relem));
+        d_conc = pl->out_c.p; d_flx = pl->out_f.p;
+    }
+    const bool forward_dir = footprint;   // fft2(norm="backward") vs ifft2(norm="forward")  solver.py:280-287
+    const bool use_library = (flags & BLDFM_FFT_LIBRARY) || !pruned_fft_supported(g, spec_f32);
+    if (use_library) {
+        const size_t field_bytes = (size_t)g.nfx * g.nfy * celem;
+        int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nfields, pl->pad_budget / field_bytes));
+        bool grew_in = false;
+        TRY(pl->pad_in.ensure((size_t)chunk * field_bytes, &grew_in));
+        TRY(pl->pad_out.ensure((size_t)chunk * field_bytes));
+        if (grew_in || pl->pad_state_elem != celem) {
+            CUDA_TRY(cudaMemsetAsync(pl->pad_in.p, 0, pl->pad_in.cap, pl->stream));
+            pl->pad_state_elem = celem;
+        }
+        for (int which = 0; which < 2; ++which) {
+            const char* spec = static_cast<const char*>(which == 0 ? pl->spec_p.p : pl->spec_q.p);
+            char* dst = static_cast<char*>(which == 0 ? d_conc : d_flx);
+            for (int64_t f0 = 0; f0 < nfields; f0 += chunk) {
+                const int nf = (int)std::min<int64_t>(chunk, nfields - f0);
+                const int gs = grid_for((int64_t)nf * nmodes, 256, pl->num_sms);
+                const int gc = grid_for((int64_t)nf * out_per_field, 256, pl->num_sms);
+                cufftHandle h;
+                if (spec_f32) {
+                    k_scatter_spectrum<float2><<<gs, 256, 0, pl->stream>>>(
+                        reinterpret_cast<const float2*>(spec + (size_t)f0 * nmodes * celem),
+                        static_cast<float2*>(pl->pad_in.p), g.nlx, g.nly, g.nfx, g.nfy, nf);
+                    TRY(get_fft_plan(pl, g.nfy, g.nfx, CUFFT_C2C, nf, &h));
+                    CUFFT_TRY(cufftExecC2C(h, static_cast<cufftComplex*>(pl->pad_in.p),
+                                           static_cast<cufftComplex*>(pl->pad_out.p),
+                                           forward_dir ? CUFFT_FORWARD : CUFFT_INVERSE));
+                    k_crop_real<float2, float><<<gc, 256, 0, pl->stream>>>(
+                        static_cast<const float2*>(pl->pad_out.p),
+                        reinterpret_cast<float*>(dst + (size_t)f0 * out_per_field * relem), g.nx, g.ny,
+                        g.px, g.py, g.nfx, g.nfy, nf);
+                } else {
+                    k_scatter_spectrum<double2><<<gs, 256, 0, pl->stream>>>(
+                        reinterpret_cast<const double2*>(spec + (size_t)f0 * nmodes * celem),
+                        static_cast<double2*>(pl->pad_in.p), g.nlx, g.nly, g.nfx, g.nfy, nf);
+                    TRY(get_fft_plan(pl, g.nfy, g.nfx, CUFFT_Z2Z, nf, &h));
+                    CUFFT_TRY(cufftExecZ2Z(h, static_cast<cufftDoubleComplex*>(pl->pad_in.p),
+                                           static_cast<cufftDoubleComplex*>(pl->pad_out.p),
+                                           forward_dir ? CUFFT_FORWARD : CUFFT_INVERSE));
+                    k_crop_real<double2, double><<<gc, 256, 0, pl->stream>>>(
+                        static_cast<const double2*>(pl->pad_out.p),
+                        reinterpret_cast<double*>(dst + (size_t)f0 * out_per_field * relem), g.nx, g.ny,
+                        g.px, g.py, g.nfx, g.nfy, nf);
+                }
+                CUDA_TRY(cudaGetLastError());
+                pl->launches += 2;
+            }
+        }
+    } else {
+        int nl = 0;
+        TRY(pl->fft_work.ensure(pruned_fft_work_bytes(g, spec_f32, nfields)));
+        TRY(pruned_fft_run(pl->stream, pl->num_sms, pl->smem_optin, g, spec_f32, forward_dir,
+                           pl->spec_p.p, pl->spec_q.p, nfields, pl->fft_work.p, d_conc, d_flx, &nl));
+        pl->launches += nl;
+    }
+    if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev[3], pl->stream));
+
+    if (!out_dev) {
+        const size_t nb = (size_t)nfields * out_per_field * relem;
+        CUDA_TRY(cudaMemcpyAsync(out.conc, d_conc, nb, cudaMemcpyDeviceToHost, pl->stream));
+        CUDA_TRY(cudaMemcpyAsync(out.flx, d_flx, nb, cudaMemcpyDeviceToHost, pl->stream));
+    }
+    if (pl->profiling) { CUDA_TRY(cudaEventRecord(pl->ev[4], pl->stream)); pl->ev_recorded = true; }
+    if (!out_dev || !(flags & BLDFM_ASYNC)) CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return BLDFM_OK;
+}
+
+__global__ void __launch_bounds__(256)
+k_fp64_peak(double* out, int iters, int use_fma, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0;
+    double a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 0.999999, c = 1e-9;
+    if (use_fma) {
+        for (int i = 0; i < iters; ++i) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    } else {
+        for (int i = 0; i < iters; ++i) {
+            a0 = a0 * m; a1 = a1 + c; a2 = a2 * m; a3 = a3 + c;
+            a4 = a4 * m; a5 = a5 + c; a6 = a6 * m; a7 = a7 + c;
+        }
+    }
+    const double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 123.456) out[0] = s;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* bldfm_version(void) { return "bldfm_b200 0.1.0 (sm_100a)"; }
+
+const char* bldfm_last_error_string(void) { return g_err.c_str(); }
+
+int bldfm_device_count(int* count)
+{
+    if (!count) return fail(BLDFM_ERR_INVALID, "count is NULL");
+    *count = 0;
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return BLDFM_OK;
+}
+
+int bldfm_geometry_init(int32_t nx, int32_t ny, double xmax, double ymax, int32_t nlx, int32_t nly,
+                        int32_t halo_is_none, double halo, bldfm_geometry* out)
+{
+    if (!out) return fail(BLDFM_ERR_INVALID, "out is NULL");
+    if (nx < 1 || ny < 1) return fail(BLDFM_ERR_INVALID, "srf_flx must be a non-empty 2D array");
+    if ((nlx % 2 != 0) || (nly % 2 != 0))                                       // solver.py:90-91
+        return fail(BLDFM_ERR_ODD_MODES, "modes must consist of even numbers.");
+    if (nlx < 1 || nly < 1) return fail(BLDFM_ERR_INVALID, "modes must be positive");
+    bldfm_geometry g{};
+    g.nx = nx; g.ny = ny; g.xmax = xmax; g.ymax = ymax;
+    g.dx = xmax / nx; g.dy = ymax / ny;                                          // :98
+    g.halo = halo_is_none ? std::max(xmax, ymax) : halo;                         // :108-109
+    const double fx = g.halo / g.dx, fy = g.halo / g.dy;
+    if (!(fx >= 0.0) || !(fy >= 0.0) || fx > 1e8 || fy > 1e8)
+        return fail(BLDFM_ERR_INVALID, "halo must be finite and non-negative");
+    g.px = (int32_t)fx; g.py = (int32_t)fy;                                      // :112-113 int() truncates
+    g.nxe = nx + 2 * g.px; g.nye = ny + 2 * g.py;                                // :119-120
+    g.nlx = nlx; g.nly = nly; g.clamped = 0;
+    if (nlx > g.nxe || nly > g.nye) { g.nlx = g.nxe; g.nly = g.nye; g.clamped = 1; }   // :122-127
+    const int dlx = (g.nxe - g.nlx) / 2, dly = (g.nye - g.nly) / 2;              // :130
+    g.nfx = g.nlx + 2 * dlx; g.nfy = g.nly + 2 * dly;                            // :269-278
+    // odd (ne - nl): the reference's transform shrinks to ne-1 (solver.py:269-278); the crop
+    // (:289-290) still yields nx columns only if there is a halo to absorb the missing column.
+    if ((g.nfx != g.nxe && g.px == 0) || (g.nfy != g.nye && g.py == 0))
+        return fail(BLDFM_ERR_ODD_PAD, "padded grid size minus modes must be even.");
+    *out = g;
+    return BLDFM_OK;
+}
+
+int bldfm_wavenumbers(const bldfm_geometry* g, double* lx, double* ly)
+{
+    if (!g || !lx || !ly) return fail(BLDFM_ERR_INVALID, "NULL argument");
+    // numpy: fftfreq(n, d) = [0..(n-1)//2, -(n//2)..-1] * (1.0/(n*d)) with d = 1.0/n   solver.py:148-149
+    // then lx = 2.0*np.pi/dx/nxe*ilx                                                   solver.py:152-153
+    for (int axis = 0; axis < 2; ++axis) {
+        const int n = axis == 0 ? g->nlx : g->nly;
+        const double dd = axis == 0 ? g->dx : g->dy;
+        const int ne = axis == 0 ? g->nxe : g->nye;
+        double* dst = axis == 0 ? lx : ly;
+        const double d = 1.0 / n;
+        const double val = 1.0 / (n * d);
+        const double fac = 2.0 * M_PI / dd / ne;
+        const int npos = (n - 1) / 2 + 1;
+        for (int i = 0; i < n; ++i) {
+            const int k = i < npos ? i : i - n;
+            const double il = (double)k * val;
+            dst[i] = fac * il;
+        }
+    }
+    return BLDFM_OK;
+}
+
+int bldfm_output_is_f32(int flags, double xm, double ym)
+{
+    if (flags & BLDFM_DOUBLE) return 0;
+    if (flags & BLDFM_FOOTPRINT) return 0;
+    return (xm * xm + ym * ym > 0.0) ? 0 : 1;
+}
+
+int bldfm_plan_create(const bldfm_geometry* g, int device, bldfm_plan** out)
+{
+    if (!g || !out) return fail(BLDFM_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(BLDFM_ERR_CUDA, std::string("no CUDA device available (bldfm_b200 has no CPU fallback): ") +
+                                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= ndev) return fail(BLDFM_ERR_INVALID, "device index out of range");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(BLDFM_ERR_CUDA, "cudaSetDevice failed");
+    bldfm_plan* pl = new bldfm_plan();
+    pl->device = device;
+    pl->g = *g;
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete pl; return fail(BLDFM_ERR_CUDA, cudaGetErrorString(e)); }
+    pl->num_sms = prop.multiProcessorCount;
+    pl->smem_optin = prop.sharedMemPerBlockOptin;
+    e = cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete pl; return fail(BLDFM_ERR_CUDA, cudaGetErrorString(e)); }
+    for (auto& ev : pl->ev) {
+        e = cudaEventCreate(&ev);
+        if (e != cudaSuccess) { bldfm_plan_destroy(pl); return fail(BLDFM_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+    // wavenumber tables
+    std::vector<double> tab((size_t)g->nlx + g->nly);
+    bldfm_wavenumbers(g, tab.data(), tab.data() + g->nlx);
+    int rc = pl->tables.ensure(tab.size() * sizeof(double));
+    if (rc != BLDFM_OK) { bldfm_plan_destroy(pl); return rc; }
+    e = cudaMemcpy(pl->tables.p, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { bldfm_plan_destroy(pl); return fail(BLDFM_ERR_CUDA, cudaGetErrorString(e)); }
+    *out = pl;
+    return BLDFM_OK;
+}
+
+int bldfm_plan_destroy(bldfm_plan* pl)
+{
+    if (!pl) return BLDFM_OK;
+    DeviceGuard guard(pl->device);
+    if (pl->stream) cudaStreamSynchronize(pl->stream);
+    for (auto& kv : pl->fft_plans) cufftDestroy(kv.second);
+    pl->tables.release(); pl->params.release(); pl->spec_p.release(); pl->spec_q.release();
+    pl->pad_in.release(); pl->pad_out.release(); pl->src_in.release(); pl->src_pad.release();
+    pl->fft_work.release(); pl->out_c.release(); pl->out_f.release();
+    for (auto& s : pl->staging) {
+        if (s.host) cudaFreeHost(s.host);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    for (auto& ev : pl->ev) if (ev) cudaEventDestroy(ev);
+    if (pl->stream) cudaStreamDestroy(pl->stream);
+    delete pl;
+    return BLDFM_OK;
+}
+
+void* bldfm_plan_stream(bldfm_plan* pl) { return pl ? (void*)pl->stream : nullptr; }
+
+int bldfm_plan_synchronize(bldfm_plan* pl)
+{
+    if (!pl) return fail(BLDFM_ERR_INVALID, "plan is NULL");
+    DeviceGuard guard(pl->device);
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return BLDFM_OK;
+}
+
+int64_t bldfm_plan_launch_count(const bldfm_plan* pl) { return pl ? pl->launches : 0; }
+
+int bldfm_plan_set_profiling(bldfm_plan* pl, int enabled)
+{
+    if (!pl) return fail(BLDFM_ERR_INVALID, "plan is NULL");
+    pl->profiling = enabled != 0;
+    pl->ev_recorded = false;
+    return BLDFM_OK;
+}
+
+int bldfm_plan_last_timings(bldfm_plan* pl, bldfm_timings* out)
+{
+    if (!pl || !out) return fail(BLDFM_ERR_INVALID, "NULL argument");
+    if (!pl->ev_recorded) return fail(BLDFM_ERR_INVALID, "no profiled solve recorded on this plan");
+    DeviceGuard guard(pl->device);
+    CUDA_TRY(cudaEventSynchronize(pl->ev[4]));
+    float f = 0, m = 0, i = 0, t = 0;
+    CUDA_TRY(cudaEventElapsedTime(&f, pl->ev[0], pl->ev[1]));
+    CUDA_TRY(cudaEventElapsedTime(&m, pl->ev[1], pl->ev[2]));
+    CUDA_TRY(cudaEventElapsedTime(&i, pl->ev[2], pl->ev[3]));
+    CUDA_TRY(cudaEventElapsedTime(&t, pl->ev[0], pl->ev[4]));
+    out->forward_ms = f; out->march_ms = m; out->inverse_ms = i; out->total_ms = t;
+    return BLDFM_OK;
+}
+
+int64_t bldfm_plan_workspace_bytes(const bldfm_plan* pl)
+{
+    if (!pl) return 0;
+    return (int64_t)(pl->tables.cap + pl->params.cap + pl->spec_p.cap + pl->spec_q.cap + pl->pad_in.cap +
+                     pl->pad_out.cap + pl->src_in.cap + pl->src_pad.cap + pl->fft_work.cap +
+                     pl->out_c.cap + pl->out_f.cap);
+}
+
+int bldfm_solve(bldfm_plan* plan, const bldfm_problem* prob, const int64_t* levels, int32_t nlv,
+                const double* srf_flx, int flags, void* conc, void* flx)
+{
+    if (!conc || !flx) return fail(BLDFM_ERR_INVALID, "output pointer is NULL");
+    SolveOut o; o.conc = conc; o.flx = flx;
+    return solve_impl(plan, 1, prob, levels, nlv, srf_flx, flags, o);
+}
+
+int bldfm_solve_batched(bldfm_plan* plan, int32_t nprob, const bldfm_problem* probs,
+                        const int64_t* levels, int32_t nlv, const double* srf_flx, int flags,
+                        void* conc, void* flx)
+{
+    if (!conc || !flx) return fail(BLDFM_ERR_INVALID, "output pointer is NULL");
+    SolveOut o; o.conc = conc; o.flx = flx;
+    return solve_impl(plan, nprob, probs, levels, nlv, srf_flx, flags, o);
+}
+
+int bldfm_solve_spectral(bldfm_plan* plan, const bldfm_problem* prob, const int64_t* levels,
+                         int32_t nlv, const double* srf_flx, int flags, double* tfftp, double* tfftq)
+{
+    if (!tfftp || !tfftq) return fail(BLDFM_ERR_INVALID, "output pointer is NULL");
+    SolveOut o; o.tfftp = tfftp; o.tfftq = tfftq;
+    return solve_impl(plan, 1, prob, levels, nlv, srf_flx, flags, o);
+}
+
+int bldfm_march(int device, int64_t M, const double* p0, const double* q0, int32_t nz,
+                const double* z, const double* u, const double* v, const double* Kx,
+                const double* Ky, const double* Kz, int32_t nlv, const int64_t* levels,
+                const double* Lx, const double* Ly, int flags,
+                double* p_top, double* q_top, double* P, double* Q)
+{
+    if (M < 1 || nz < 2 || nlv < 0) return fail(BLDFM_ERR_INVALID, "bad sizes");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(BLDFM_ERR_CUDA, "no CUDA device available (bldfm_b200 has no CPU fallback)");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(BLDFM_ERR_CUDA, "cudaSetDevice failed");
+    const int S = nz - 1;
+    bldfm_problem pb{};
+    pb.z = z; pb.u = u; pb.v = v; pb.Kx = Kx; pb.Ky = Ky; pb.Kz = Kz; pb.nz = nz;
+    std::vector<LevelCoef> lc((size_t)S);
+    fill_coefs(pb, lc.data());
+    // membership only (out-of-range levels simply never match, like `i in levels`)
+    std::vector<int32_t> row_of((size_t)nz, -1);
+    int row = 0;
+    for (int i = 0; i < nz; ++i) {
+        bool hit = false;
+        for (int k = 0; k < nlv; ++k) if (levels[k] == i) { hit = true; break; }
+        if (hit) row_of[(size_t)i] = row++;
+    }
+    const size_t cb = sizeof(double2) * (size_t)M;
+    const size_t lb = sizeof(double2) * (size_t)M * (size_t)std::max(nlv, 1);
+    char* d = nullptr;
+    const size_t off_lc = 0, off_row = off_lc + sizeof(LevelCoef) * (size_t)S;
+    size_t off = off_row + sizeof(int32_t) * (size_t)nz;
+    off = (off + 255) & ~(size_t)255;
+    const size_t off_p0 = off; off += cb;
+    const size_t off_q0 = off; off += cb;
+    const size_t off_lx = off; off += sizeof(double) * (size_t)M;
+    const size_t off_ly = off; off += sizeof(double) * (size_t)M;
+    off = (off + 255) & ~(size_t)255;
+    const size_t off_pt = off; off += cb;
+    const size_t off_qt = off; off += cb;
+    const size_t off_P = off; off += lb;
+    const size_t off_Q = off; off += lb;
+    CUDA_TRY(cudaMalloc(&d, off));
+    int rc = BLDFM_OK;
+    do {
+#define MARCH_TRY(expr)                                                                          \
+    if ((e = (expr)) != cudaSuccess) { rc = fail(BLDFM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e)); break; }
+        MARCH_TRY(cudaMemcpy(d + off_lc, lc.data(), sizeof(LevelCoef) * (size_t)S, cudaMemcpyHostToDevice));
+        MARCH_TRY(cudaMemcpy(d + off_row, row_of.data(), sizeof(int32_t) * (size_t)nz, cudaMemcpyHostToDevice));
+        MARCH_TRY(cudaMemcpy(d + off_p0, p0, cb, cudaMemcpyHostToDevice));
+        MARCH_TRY(cudaMemcpy(d + off_q0, q0, cb, cudaMemcpyHostToDevice));
+        MARCH_TRY(cudaMemcpy(d + off_lx, Lx, sizeof(double) * (size_t)M, cudaMemcpyHostToDevice));
+        MARCH_TRY(cudaMemcpy(d + off_ly, Ly, sizeof(double) * (size_t)M, cudaMemcpyHostToDevice));
+        MARCH_TRY(cudaMemset(d + off_P, 0, 2 * lb));
+        const size_t smem = sizeof(LevelCoef) * (size_t)S + sizeof(int32_t) * (size_t)nz;
+        const unsigned grid = (unsigned)((M + kMarchThreads - 1) / kMarchThreads);
+        if (flags & BLDFM_MARCH_FMA) {
+            MARCH_TRY(cudaFuncSetAttribute(k_ivp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            k_ivp<true><<<grid, kMarchThreads, smem>>>(M, S, (const LevelCoef*)(d + off_lc), (const int32_t*)(d + off_row),
+                (const double2*)(d + off_p0), (const double2*)(d + off_q0), (const double*)(d + off_lx),
+                (const double*)(d + off_ly), (double2*)(d + off_pt), (double2*)(d + off_qt),
+                (double2*)(d + off_P), (double2*)(d + off_Q));
+        } else {
+            MARCH_TRY(cudaFuncSetAttribute(k_ivp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            k_ivp<false><<<grid, kMarchThreads, smem>>>(M, S, (const LevelCoef*)(d + off_lc), (const int32_t*)(d + off_row),
+                (const double2*)(d + off_p0), (const double2*)(d + off_q0), (const double*)(d + off_lx),
+                (const double*)(d + off_ly), (double2*)(d + off_pt), (double2*)(d + off_qt),
+                (double2*)(d + off_P), (double2*)(d + off_Q));
+        }
+        MARCH_TRY(cudaGetLastError());
+        MARCH_TRY(cudaDeviceSynchronize());
+        MARCH_TRY(cudaMemcpy(p_top, d + off_pt, cb, cudaMemcpyDeviceToHost));
+        MARCH_TRY(cudaMemcpy(q_top, d + off_qt, cb, cudaMemcpyDeviceToHost));
+        if (nlv > 0) {
+            MARCH_TRY(cudaMemcpy(P, d + off_P, lb, cudaMemcpyDeviceToHost));
+            MARCH_TRY(cudaMemcpy(Q, d + off_Q, lb, cudaMemcpyDeviceToHost));
+        }
+#undef MARCH_TRY
+    } while (0);
+    cudaFree(d);
+    return rc;
+}
+
+int bldfm_host_alloc(int64_t bytes, void** out)
+{
+    if (!out || bytes < 0) return fail(BLDFM_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaMallocHost(out, (size_t)std::max<int64_t>(bytes, 1)));
+    return BLDFM_OK;
+}
+
+int bldfm_host_free(void* p)
+{
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return BLDFM_OK;
+}
+
+int bldfm_device_alloc(int device, int64_t bytes, void** out)
+{
+    if (!out || bytes < 0) return fail(BLDFM_ERR_INVALID, "bad argument");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(BLDFM_ERR_CUDA, "cudaSetDevice failed");
+    CUDA_TRY(cudaMalloc(out, (size_t)std::max<int64_t>(bytes, 1)));
+    return BLDFM_OK;
+}
+
+int bldfm_device_free(int device, void* p)
+{
+    DeviceGuard guard(device);
+    if (p) CUDA_TRY(cudaFree(p));
+    return BLDFM_OK;
+}
+
+int bldfm_memcpy_d2h(int device, void* dst_host, const void* src_dev, int64_t bytes)
+{
+    DeviceGuard guard(device);
+    CUDA_TRY(cudaMemcpy(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return BLDFM_OK;
+}
+
+int bldfm_memcpy_h2d(int device, void* dst_dev, const void* src_host, int64_t bytes)
+{
+    DeviceGuard guard(device);
+    CUDA_TRY(cudaMemcpy(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice));
+    return BLDFM_OK;
+}
+
+int bldfm_fp64_peak(int device, int use_fma, int iters, double* gops_per_s)
+{
+    if (!gops_per_s || iters < 1) return fail(BLDFM_ERR_INVALID, "bad argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(BLDFM_ERR_CUDA, "no CUDA device available");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(BLDFM_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    double* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    k_fp64_peak<<<blocks, threads>>>(d, iters / 4 + 1, use_fma, 1.0);   // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0));
+        k_fp64_peak<<<blocks, threads>>>(d, iters, use_fma, 1.0);
+        CUDA_TRY(cudaEventRecord(e1));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double ops = (double)blocks * threads * 8.0 * iters;
+        best = std::max(best, ops / (ms * 1e-3) * 1e-9);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *gops_per_s = best;
+    return BLDFM_OK;
+}
+
+}  // extern "C"

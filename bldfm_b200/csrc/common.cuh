@@ -1,0 +1,50 @@
+// common.cuh -- shared device/host definitions for libbldfm_b200 (sm_100a).
+//
+// This translation unit family is compiled with --fmad=false: a plain `a*b+c` is NEVER contracted.
+// Wherever a fused multiply-add is wanted it is written as an explicit fma().  That keeps the
+// rounding of every operation under our control, which the linear-shooting combine needs
+// (round-off is amplified by e^{2*kappa}).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bldfm {
+
+// Per-level scalars of one march step i (solver.py:357-364), precomputed on the host in the
+// reference's operation order and staged in shared memory by the march kernels.
+// 16 doubles = 128 B so that a level is four 32 B sectors and every field is LDS.128-friendly.
+struct __align__(16) LevelCoef {
+    double Kx, Ky;     // Kx[i], Ky[i]
+    double u, v;       // u[i], v[i]
+    double s, h;       // 0.5*Kzinv ; dz[i]
+    double h2, h3;     // dz*dz ; (dz*dz)*dz
+    double s6, s61;    // (1/6)*(Kzinv*Kzinv) ; (1/6)*Kzinv
+    double c0, w;      // (-Kzinv)*dz ; trapezoid weight 0.5/Kz[i] + 0.5/Kz[i+1]   (solver.py:248)
+    double sh2, s6h3;  // FMA mode only: s*h2 ; s6*h3
+    double s61h3, pad; // FMA mode only: s61*h3
+};
+static_assert(sizeof(LevelCoef) == 128, "LevelCoef must be 128 bytes");
+
+// One march group: a unique (z, profiles, srf_bg_conc).  Towers that share it differ only by the
+// phase shift.
+struct GroupDesc {
+    int32_t S;            // number of march steps = nz - 1
+    int32_t tow_begin;    // first entry in the tower list
+    int32_t tow_count;    // number of towers / output slots fed by this march
+    int32_t pad;
+    double kz_top;        // Kz[nz-1]                          solver.py:228
+    double kinv_top;      // 1.0/Kz[nz-1]                      solver.py:164
+    double kxk, kyk;      // Kx[nz-1]*Kzinv, Ky[nz-1]*Kzinv    solver.py:165-166
+    double c1, c2;        // u[nz-1]*Kzinv, v[nz-1]*Kzinv      solver.py:172-173
+    double p000;          // srf_bg_conc                       solver.py:83
+    double h_analytic;    // z[level]-z[0] (analytic branch)   solver.py:197
+};
+
+struct TowerDesc {
+    double sx, sy;        // phase = lx*sx + ly*sy             solver.py:255,260
+    int32_t shift;        // 0: no phase shift applied         solver.py:254-262
+    int32_t slot;         // output problem index
+};
+
+}  // namespace bldfm

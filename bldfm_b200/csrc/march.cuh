@@ -1,0 +1,458 @@
+// march.cuh -- the per-(kx,ky)-mode vertical march of BLDFM on sm_100a.
+//
+// Replaces ivp_solver (src/bldfm/solver.py:307-374) AND the numpy stages around it that the
+// reference runs as separate array passes: top eigenvalue (solver.py:164-174), shooting
+// coefficient + combination (:228-235), the degenerate (0,0) mode (:239-251) and the phase
+// shift (:254-262).  One thread owns one Fourier mode and carries BOTH initial-value problems in
+// registers; per-level coefficients are staged once per CTA in shared memory; only the combined,
+// shifted spectra of the requested levels are written (coalesced, 16 B per thread).
+//
+// Arithmetic modes
+//   FMA=false (default): every operation of the march is an individually rounded IEEE binary64
+//       op in the reference's order -> bitwise equal to the reference's numba code.
+//   FMA=true  (opt-in) : algebraically identical, contracted into FMAs (46 instead of 85 FP64
+//       instructions per mode-step).  Differs from the reference at the self-noise level.
+#pragma once
+
+#include "common.cuh"
+
+namespace bldfm {
+
+// ------------------------------------------------------------------------------------------------
+// complex helpers mirroring the numpy kernels that surround the march
+// ------------------------------------------------------------------------------------------------
+
+// numpy contiguous complex128 multiply: re = fma(ar,br,-(ai*bi)), im = fma(ar,bi,ai*br)
+__device__ __forceinline__ void cmul_np(double ar, double ai, double br, double bi, double& cr,
+                                        double& ci)
+{
+    cr = fma(ar, br, -(ai * bi));
+    ci = fma(ar, bi, ai * br);
+}
+
+// numpy complex128 divide: Smith's algorithm, no FMA
+__device__ __forceinline__ void cdiv_np(double ar, double ai, double br, double bi, double& cr,
+                                        double& ci)
+{
+    if (fabs(br) >= fabs(bi)) {
+        const double rat = bi / br;
+        const double scl = 1.0 / (br + bi * rat);
+        cr = (ar + ai * rat) * scl;
+        ci = (ai - ar * rat) * scl;
+    } else {
+        const double rat = br / bi;
+        const double scl = 1.0 / (bi + br * rat);
+        cr = (ar * rat + ai) * scl;
+        ci = (ai * rat - ar) * scl;
+    }
+}
+
+// hypot to (almost always) correct rounding: x*x + y*y in double-double, one Newton correction.
+__device__ __forceinline__ double hypot_cr(double x, double y)
+{
+    const double x2 = x * x, ex = fma(x, x, -x2);
+    const double y2 = y * y, ey = fma(y, y, -y2);
+    const double s = x2 + y2;
+    const double bb = s - x2;
+    const double es = (x2 - (s - bb)) + (y2 - bb);   // two-sum error
+    const double h = sqrt(s);
+    if (h == 0.0) return 0.0;
+    const double r = fma(-h, h, s) + (es + ex + ey); // s_exact - h*h
+    return h + r / (2.0 * h);
+}
+
+// csqrt as glibc computes it for finite, non-tiny arguments (numpy's np.sqrt on complex128 calls it)
+__device__ __forceinline__ void csqrt_np(double re, double im, double& sr, double& si)
+{
+    if (re == 0.0 && im == 0.0) { sr = 0.0; si = im; return; }
+    const double d = hypot_cr(re, im);
+    double r, s;
+    if (re > 0.0) {
+        r = sqrt(0.5 * (d + re));
+        s = 0.5 * (im / r);
+    } else {
+        s = sqrt(0.5 * (d - re));
+        r = fabs(0.5 * (im / s));
+    }
+    sr = r;
+    si = copysign(s, im);
+}
+
+// ------------------------------------------------------------------------------------------------
+// one march step
+// ------------------------------------------------------------------------------------------------
+struct Prop { double ar, ai, br, bi, cr, ci; };   // a (= d), b, c of solver.py:361-364
+
+template <bool FMA>
+__device__ __forceinline__ void propagator(const LevelCoef& c, double lx, double ly, double lx2,
+                                           double ly2, Prop& P)
+{
+    if (!FMA) {
+        // exact operation order of SURVEY.md A.2 ; --fmad=false keeps each op individually rounded
+        const double tr = -(c.Kx * lx2 + c.Ky * ly2);
+        const double ti = -(c.u * lx) - (c.v * ly);
+        P.ar = 1.0 - (c.s * tr) * c.h2;
+        P.ai = 0.0 - (c.s * ti) * c.h2;
+        P.br = c.c0 - (c.s6 * tr) * c.h3;
+        P.bi = 0.0 - (c.s6 * ti) * c.h3;
+        const double t2r = tr * tr - ti * ti;
+        const double m = tr * ti;
+        const double t2i = m + m;                  // == tr*ti + ti*tr bitwise
+        P.cr = tr * c.h - (c.s61 * t2r) * c.h3;
+        P.ci = ti * c.h - (c.s61 * t2i) * c.h3;
+    } else {
+        const double tr = -fma(c.Kx, lx2, c.Ky * ly2);
+        const double ti = -fma(c.u, lx, c.v * ly);
+        P.ar = fma(-c.sh2, tr, 1.0);
+        P.ai = -(c.sh2 * ti);
+        P.br = fma(-c.s6h3, tr, c.c0);
+        P.bi = -(c.s6h3 * ti);
+        // c = T*(h - s61h3*T)
+        const double gr = fma(-c.s61h3, tr, c.h);
+        const double gi = -(c.s61h3 * ti);
+        P.cr = fma(tr, gr, -(ti * gi));
+        P.ci = fma(tr, gi, ti * gr);
+    }
+}
+
+template <bool FMA>
+__device__ __forceinline__ void apply(const Prop& P, double& pr, double& pi, double& qr, double& qi)
+{
+    double npr, npi, nqr, nqi;
+    if (!FMA) {
+        npr = (P.ar * pr - P.ai * pi) + (P.br * qr - P.bi * qi);
+        npi = (P.ar * pi + P.ai * pr) + (P.br * qi + P.bi * qr);
+        nqr = (P.cr * pr - P.ci * pi) + (P.ar * qr - P.ai * qi);
+        nqi = (P.cr * pi + P.ci * pr) + (P.ar * qi + P.ai * qr);
+    } else {
+        npr = fma(P.ar, pr, fma(-P.ai, pi, fma(P.br, qr, -(P.bi * qi))));
+        npi = fma(P.ar, pi, fma(P.ai, pr, fma(P.br, qi, P.bi * qr)));
+        nqr = fma(P.cr, pr, fma(-P.ci, pi, fma(P.ar, qr, -(P.ai * qi))));
+        nqi = fma(P.cr, pi, fma(P.ci, pr, fma(P.ar, qi, P.ai * qr)));
+    }
+    pr = npr; pi = npi; qr = nqr; qi = nqi;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused march kernel
+// ------------------------------------------------------------------------------------------------
+struct MarchArgs {
+    int32_t nlx, nly;          // retained modes
+    int32_t nlv;               // output rows
+    int32_t coef_stride;       // LevelCoef entries per group (= max steps)
+    int32_t nrow_of;           // entries in row_of (= max nz)
+    int32_t snap_level;        // single-row path: level to snapshot, -1 = none visited
+    int32_t last_level;        // multi-row path: highest requested level
+    int32_t single;            // precision == "single": round tfftp/tfftq to complex64 values
+    int32_t out_f32;           // spectra stored as float2 (no shift applied, single)
+    int32_t footprint;
+    int32_t src_pitch;         // row pitch (complex elements) of src_spec
+    int32_t src_nfx, src_nfy;  // size of the forward spectrum for index wrapping
+    double  q0_const;          // (1/nxe)/nye                                   solver.py:134
+    double  src_scale;         // 1/(nxe*nye)   norm="forward"                  solver.py:136
+    const double2*   src_spec; // forward spectrum of the padded source (non-footprint)
+    const LevelCoef* coef;     // [ngroups][coef_stride]
+    const int32_t*   row_of;   // [nrow_of]  level -> output row or -1
+    const GroupDesc* groups;
+    const TowerDesc* towers;
+    const double*    lx;       // [nlx]
+    const double*    ly;       // [nly]
+    void* outp;                // [slot][row][nly][nlx] complex (double2 | float2)
+    void* outq;
+    int64_t slot_stride;       // complex elements between output slots (= nlv*nly*nlx)
+};
+
+__device__ __forceinline__ double round_f32(double x) { return (double)(float)x; }
+
+struct Emit {
+    const MarchArgs& a;
+    const GroupDesc& gd;
+    const TowerDesc* tw;
+    int64_t mode;
+    double lx, ly;
+    double cs0, sn0;     // phase factor of the group's first tower, hoisted out of the row loop
+
+    __device__ __forceinline__ Emit(const MarchArgs& a_, const GroupDesc& gd_, int64_t mode_,
+                                    double lx_, double ly_)
+        : a(a_), gd(gd_), tw(a_.towers + gd_.tow_begin), mode(mode_), lx(lx_), ly(ly_),
+          cs0(1.0), sn0(0.0)
+    {
+        if (gd.tow_count > 0 && tw[0].shift) phase(tw[0], cs0, sn0);
+    }
+
+    // exp(1j*(Lx*sx + Ly*sy))                                              solver.py:255 / :260
+    __device__ __forceinline__ void phase(const TowerDesc& td, double& cs, double& sn) const
+    {
+        const double th = lx * td.sx + ly * td.sy;
+        sincos(th, &sn, &cs);
+    }
+
+    // store one combined (p,q) pair into row `row` of every tower slot of the group
+    __device__ __forceinline__ void operator()(int row, double pr, double pi, double qr,
+                                               double qi) const
+    {
+        if (a.single) {
+            pr = round_f32(pr); pi = round_f32(pi); qr = round_f32(qr); qi = round_f32(qi);
+        }
+        const int64_t rowoff = (int64_t)row * a.nly * a.nlx + mode;
+        for (int t = 0; t < gd.tow_count; ++t) {
+            const TowerDesc td = tw[t];
+            double opr = pr, opi = pi, oqr = qr, oqi = qi;
+            if (td.shift) {
+                double sn = sn0, cs = cs0;
+                if (t > 0) phase(td, cs, sn);
+                cmul_np(pr, pi, cs, sn, opr, opi);
+                cmul_np(qr, qi, cs, sn, oqr, oqi);
+            }
+            const int64_t o = (int64_t)td.slot * a.slot_stride + rowoff;
+            if (a.out_f32) {
+                reinterpret_cast<float2*>(a.outp)[o] = make_float2((float)opr, (float)opi);
+                reinterpret_cast<float2*>(a.outq)[o] = make_float2((float)oqr, (float)oqi);
+            } else {
+                reinterpret_cast<double2*>(a.outp)[o] = make_double2(opr, opi);
+                reinterpret_cast<double2*>(a.outq)[o] = make_double2(oqr, oqi);
+            }
+        }
+    }
+};
+
+constexpr int kMarchThreads = 128;
+
+// grid = (ceil(nlx*nly / kMarchThreads), ngroups) ; dynamic smem = coef_stride*128 + nrow_of*4
+template <bool FMA, bool MULTI>
+__global__ void __launch_bounds__(kMarchThreads)
+k_march(const MarchArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LevelCoef* sc = reinterpret_cast<LevelCoef*>(smem_raw);
+    int32_t* srow = reinterpret_cast<int32_t*>(sc + a.coef_stride);
+
+    const GroupDesc gd = a.groups[blockIdx.y];
+    const int S = gd.S;
+    {
+        const double2* src = reinterpret_cast<const double2*>(a.coef + (size_t)blockIdx.y * a.coef_stride);
+        double2* dst = reinterpret_cast<double2*>(sc);
+        for (int i = threadIdx.x; i < S * 8; i += kMarchThreads) dst[i] = src[i];
+        for (int i = threadIdx.x; i < a.nrow_of; i += kMarchThreads) srow[i] = a.row_of[i];
+    }
+    __syncthreads();
+
+    const int64_t mode = (int64_t)blockIdx.x * kMarchThreads + threadIdx.x;
+    if (mode >= (int64_t)a.nlx * a.nly) return;
+    const int ky = (int)(mode / a.nlx);
+    const int kx = (int)(mode - (int64_t)ky * a.nlx);
+    const double lx = a.lx[kx], ly = a.ly[ky];
+
+    // source spectrum of this mode (solver.py:134 / :136-145)
+    double q0r, q0i;
+    if (a.footprint) {
+        q0r = a.q0_const; q0i = 0.0;
+    } else {
+        const int pk = (a.nlx + 1) / 2, pl = (a.nly + 1) / 2;
+        const int wx = kx < pk ? kx : kx - a.nlx + a.src_nfx;
+        const int wy = ky < pl ? ky : ky - a.nly + a.src_nfy;
+        const double2 sv = a.src_spec[(size_t)wy * a.src_pitch + wx];
+        q0r = sv.x * a.src_scale; q0i = sv.y * a.src_scale;
+    }
+
+    const Emit emit(a, gd, mode, lx, ly);
+
+    if (mode == 0) {
+        // degenerate mode: flux constant, concentration by the trapezoid rule (solver.py:190-191,239-251)
+        double pr = gd.p000, pi = 0.0;
+        bool any = false;
+        for (int i = 0; i < S; ++i) {
+            if (srow[i] >= 0) { emit(srow[i], pr, pi, q0r, q0i); any = true; }
+            pr = pr - (q0r * sc[i].h) * sc[i].w;
+            pi = pi - (q0i * sc[i].h) * sc[i].w;
+        }
+        if (srow[S] >= 0) { emit(srow[S], pr, pi, q0r, q0i); any = true; }
+        // rows never visited keep tfftp[0,0,0]=p000 (row 0) / 0 and tfftq[:,0,0]=tfftq0[0,0]
+        int visited = 0;
+        for (int i = 0; i <= S; ++i) visited += (srow[i] >= 0);
+        for (int r = visited; r < a.nlv; ++r)
+            emit(r, (r == 0 && !any) ? gd.p000 : 0.0, 0.0, q0r, q0i);
+        return;
+    }
+
+    const double lx2 = lx * lx, ly2 = ly * ly;
+
+    // IVP1 from (1,0), IVP2 from (0,q0)   (solver.py:220-226)
+    double p1r = 1.0, p1i = 0.0, q1r = 0.0, q1i = 0.0;
+    double p2r = 0.0, p2i = 0.0, q2r = q0r, q2i = q0i;
+    // single-row snapshot registers
+    double s1pr = 0.0, s1pi = 0.0, s1qr = 0.0, s1qi = 0.0;
+    double s2pr = 0.0, s2pi = 0.0, s2qr = 0.0, s2qi = 0.0;
+
+    Prop P;
+    if (!MULTI) {
+        const int snap = a.snap_level;
+        const int n1 = (snap >= 0 && snap <= S) ? snap : S;
+#pragma unroll 2
+        for (int i = 0; i < n1; ++i) {
+            propagator<FMA>(sc[i], lx, ly, lx2, ly2, P);
+            apply<FMA>(P, p1r, p1i, q1r, q1i);
+            apply<FMA>(P, p2r, p2i, q2r, q2i);
+        }
+        if (snap >= 0 && snap <= S) {
+            s1pr = p1r; s1pi = p1i; s1qr = q1r; s1qi = q1i;
+            s2pr = p2r; s2pi = p2i; s2qr = q2r; s2qi = q2i;
+        }
+#pragma unroll 2
+        for (int i = n1; i < S; ++i) {
+            propagator<FMA>(sc[i], lx, ly, lx2, ly2, P);
+            apply<FMA>(P, p1r, p1i, q1r, q1i);
+            apply<FMA>(P, p2r, p2i, q2r, q2i);
+        }
+    } else {
+#pragma unroll 2
+        for (int i = 0; i < S; ++i) {
+            propagator<FMA>(sc[i], lx, ly, lx2, ly2, P);
+            apply<FMA>(P, p1r, p1i, q1r, q1i);
+            apply<FMA>(P, p2r, p2i, q2r, q2i);
+        }
+    }
+
+    // radiation condition at the top: eig, alpha (solver.py:164-174, 228-230)
+    double alr, ali;
+    {
+        const double are = gd.kxk * lx2 + gd.kyk * ly2;
+        const double aim = gd.c1 * lx + gd.c2 * ly;
+        double er, ei;
+        csqrt_np(are, aim, er, ei);
+        const double ker = gd.kz_top * er, kei = gd.kz_top * ei;
+        double t2r, t2i, t1r, t1i;
+        cmul_np(ker, kei, p2r, p2i, t2r, t2i);
+        cmul_np(ker, kei, p1r, p1i, t1r, t1i);
+        const double nr = -(q2r - t2r), ni = -(q2i - t2i);
+        const double dr = q1r - t1r, di = q1i - t1i;
+        cdiv_np(nr, ni, dr, di, alr, ali);
+    }
+
+    if (!MULTI) {
+        // p = alpha*P1 + P2 ; q = alpha*Q1 + Q2   (solver.py:234-235)
+        double mr, mi, pr, pi, qr, qi;
+        cmul_np(alr, ali, s1pr, s1pi, mr, mi); pr = mr + s2pr; pi = mi + s2pi;
+        cmul_np(alr, ali, s1qr, s1qi, mr, mi); qr = mr + s2qr; qi = mi + s2qi;
+        if (a.nlv > 0) emit(0, pr, pi, qr, qi);
+        for (int r = 1; r < a.nlv; ++r) emit(r, 0.0, 0.0, 0.0, 0.0);
+    } else {
+        // re-march (deterministic, so bitwise the same states) and emit each requested row
+        p1r = 1.0; p1i = 0.0; q1r = 0.0; q1i = 0.0;
+        p2r = 0.0; p2i = 0.0; q2r = q0r; q2i = q0i;
+        const int last = a.last_level < S ? a.last_level : S;
+        int rows = 0;
+        for (int i = 0; i <= last; ++i) {
+            const int row = srow[i];
+            if (row >= 0) {
+                double mr, mi, pr, pi, qr, qi;
+                cmul_np(alr, ali, p1r, p1i, mr, mi); pr = mr + p2r; pi = mi + p2i;
+                cmul_np(alr, ali, q1r, q1i, mr, mi); qr = mr + q2r; qi = mi + q2i;
+                emit(row, pr, pi, qr, qi);
+                ++rows;
+            }
+            if (i < last) {
+                propagator<FMA>(sc[i], lx, ly, lx2, ly2, P);
+                apply<FMA>(P, p1r, p1i, q1r, q1i);
+                apply<FMA>(P, p2r, p2i, q2r, q2i);
+            }
+        }
+        for (int r = rows; r < a.nlv; ++r) emit(r, 0.0, 0.0, 0.0, 0.0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// analytic branch for constant profiles (solver.py:193-202), one level
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMarchThreads)
+k_analytic(const MarchArgs a)
+{
+    const GroupDesc gd = a.groups[blockIdx.y];
+    const int64_t mode = (int64_t)blockIdx.x * kMarchThreads + threadIdx.x;
+    if (mode >= (int64_t)a.nlx * a.nly) return;
+    const int ky = (int)(mode / a.nlx);
+    const int kx = (int)(mode - (int64_t)ky * a.nlx);
+    const double lx = a.lx[kx], ly = a.ly[ky];
+    double q0r, q0i;
+    if (a.footprint) {
+        q0r = a.q0_const; q0i = 0.0;
+    } else {
+        const int pk = (a.nlx + 1) / 2, pl = (a.nly + 1) / 2;
+        const int wx = kx < pk ? kx : kx - a.nlx + a.src_nfx;
+        const int wy = ky < pl ? ky : ky - a.nly + a.src_nfy;
+        const double2 sv = a.src_spec[(size_t)wy * a.src_pitch + wx];
+        q0r = sv.x * a.src_scale; q0i = sv.y * a.src_scale;
+    }
+    const Emit emit(a, gd, mode, lx, ly);
+    const double h = gd.h_analytic;
+    if (mode == 0) {
+        // tfftp[:,0,0] = p000 - tfftq0[0,0]*Kzinv*h ; tfftq[:,0,0] = tfftq0[0,0]
+        const double pr = gd.p000 - (q0r * gd.kinv_top) * h;
+        const double pi = 0.0 - (q0i * gd.kinv_top) * h;
+        emit(0, pr, pi, q0r, q0i);
+        return;
+    }
+    const double lx2 = lx * lx, ly2 = ly * ly;
+    const double are = gd.kxk * lx2 + gd.kyk * ly2;
+    const double aim = gd.c1 * lx + gd.c2 * ly;
+    double er, ei;
+    csqrt_np(are, aim, er, ei);
+    // tfftq = tfftq0 * exp(-eig*h)
+    const double xr = (-er) * h, xi = (-ei) * h;
+    const double mag = exp(xr);
+    double sn, cs;
+    sincos(xi, &sn, &cs);
+    double qr, qi;
+    cmul_np(q0r, q0i, mag * cs, mag * sn, qr, qi);
+    if (a.single) { qr = round_f32(qr); qi = round_f32(qi); }
+    // tfftp = tfftq * Kzinv / eig
+    double pr, pi;
+    cdiv_np(qr * gd.kinv_top, qi * gd.kinv_top, er, ei, pr, pi);
+    emit(0, pr, pi, qr, qi);
+}
+
+// ------------------------------------------------------------------------------------------------
+// plain ivp_solver (solver.py:307-374) for isolated parity tests: arbitrary (p0,q0,Lx,Ly) per mode,
+// raw snapshots P,Q [nlv][M].  Same propagator/apply code as the fused kernel.
+// ------------------------------------------------------------------------------------------------
+template <bool FMA>
+__global__ void __launch_bounds__(kMarchThreads)
+k_ivp(int64_t M, int S, const LevelCoef* __restrict__ coef, const int32_t* __restrict__ row_of,
+      const double2* __restrict__ p0, const double2* __restrict__ q0,
+      const double* __restrict__ Lx, const double* __restrict__ Ly,
+      double2* __restrict__ p_top, double2* __restrict__ q_top,
+      double2* __restrict__ Pout, double2* __restrict__ Qout)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LevelCoef* sc = reinterpret_cast<LevelCoef*>(smem_raw);
+    int32_t* srow = reinterpret_cast<int32_t*>(sc + S);
+    {
+        const double2* src = reinterpret_cast<const double2*>(coef);
+        double2* dst = reinterpret_cast<double2*>(sc);
+        for (int i = threadIdx.x; i < S * 8; i += kMarchThreads) dst[i] = src[i];
+        for (int i = threadIdx.x; i <= S; i += kMarchThreads) srow[i] = row_of[i];
+    }
+    __syncthreads();
+    const int64_t m = (int64_t)blockIdx.x * kMarchThreads + threadIdx.x;
+    if (m >= M) return;
+    const double lx = Lx[m], ly = Ly[m];
+    const double lx2 = lx * lx, ly2 = ly * ly;
+    double pr = p0[m].x, pi = p0[m].y, qr = q0[m].x, qi = q0[m].y;
+    Prop P;
+    for (int i = 0; i < S; ++i) {
+        if (srow[i] >= 0) {
+            Pout[(size_t)srow[i] * M + m] = make_double2(pr, pi);
+            Qout[(size_t)srow[i] * M + m] = make_double2(qr, qi);
+        }
+        propagator<FMA>(sc[i], lx, ly, lx2, ly2, P);
+        apply<FMA>(P, pr, pi, qr, qi);
+    }
+    if (srow[S] >= 0) {
+        Pout[(size_t)srow[S] * M + m] = make_double2(pr, pi);
+        Qout[(size_t)srow[S] * M + m] = make_double2(qr, qi);
+    }
+    p_top[m] = make_double2(pr, pi);
+    q_top[m] = make_double2(qr, qi);
+}
+
+}  // namespace bldfm

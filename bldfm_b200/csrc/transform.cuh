@@ -1,0 +1,72 @@
+// transform.cuh -- data-movement kernels around the horizontal transforms (K1, K3, K9, K11).
+//
+// Replaces np.pad (solver.py:116), fftshift/slice/ifftshift (:139-145), fftshift/pad/ifftshift
+// (:265-278) and the crop + .real (:282-290) of the reference, each of which is a separate full
+// array pass there.  Here truncation is an index map folded into the march kernel's loads, and
+// un-truncation / crop are single gather/scatter kernels around the library transform
+// (BLDFM_FFT_LIBRARY path) or folded into the pruned in-house transform (fft.cuh).
+#pragma once
+
+#include "common.cuh"
+
+namespace bldfm {
+
+// signed-frequency wrap: truncated index i (fftfreq order, length nl) -> index in a length-nf axis
+__device__ __forceinline__ int wrap_freq(int i, int nl, int nf)
+{
+    return i < (nl + 1) / 2 ? i : i - nl + nf;
+}
+
+// K1: embed q0[ny][nx] (real) into a zero halo as complex [nye][nxe]                solver.py:116
+__global__ void __launch_bounds__(256)
+k_pad_source(const double* __restrict__ q0, double2* __restrict__ dst, int nx, int ny, int px,
+             int py, int nxe, int nye)
+{
+    const int64_t n = (int64_t)nxe * nye;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(i / nxe), x = (int)(i - (int64_t)y * nxe);
+        const int sy = y - py, sx = x - px;
+        double v = 0.0;
+        if (sy >= 0 && sy < ny && sx >= 0 && sx < nx) v = q0[(size_t)sy * nx + sx];
+        dst[i] = make_double2(v, 0.0);
+    }
+}
+
+// K9: scatter compact spectra [nfields][nly][nlx] into [nfields][nfy][nfx] at the wrapped
+// positions.  Everything else in `dst` is zero and stays zero between solves (static halo).
+template <typename C>
+__global__ void __launch_bounds__(256)
+k_scatter_spectrum(const C* __restrict__ src, C* __restrict__ dst, int nlx, int nly, int nfx,
+                   int nfy, int nfields)
+{
+    const int64_t per = (int64_t)nlx * nly;
+    const int64_t n = per * nfields;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i / per);
+        const int64_t r = i - (int64_t)f * per;
+        const int ky = (int)(r / nlx), kx = (int)(r - (int64_t)ky * nlx);
+        const int wy = wrap_freq(ky, nly, nfy), wx = wrap_freq(kx, nlx, nfx);
+        dst[((size_t)f * nfy + wy) * nfx + wx] = src[i];
+    }
+}
+
+// K11: crop [py:py+ny, px:px+nx] and keep the real part                          solver.py:282-290
+template <typename C, typename R>
+__global__ void __launch_bounds__(256)
+k_crop_real(const C* __restrict__ src, R* __restrict__ dst, int nx, int ny, int px, int py,
+            int nfx, int nfy, int nfields)
+{
+    const int64_t per = (int64_t)nx * ny;
+    const int64_t n = per * nfields;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i / per);
+        const int64_t r = i - (int64_t)f * per;
+        const int y = (int)(r / nx), x = (int)(r - (int64_t)y * nx);
+        dst[i] = src[((size_t)f * nfy + (py + y)) * nfx + (px + x)].x;
+    }
+}
+
+}  // namespace bldfm

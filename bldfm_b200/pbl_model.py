@@ -1,0 +1,140 @@
+"""Host-side input producer: MOST / MOSTM / CONSTANT / OAAHOC vertical profiles.
+
+Same signature and return structure as the reference's ``bldfm.pbl_model.vertical_profiles``
+(src/bldfm/pbl_model.py:8-204) so that callers (interface.py:77-95, examples, tests) are unchanged.
+It is O(nz) work on 1-D arrays and stays on the host; the hot path
+consumes its output.  ``vertical_profiles_batch`` is the vectorised form used by the batched
+drivers (one call for B met conditions).
+"""
+
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+logger = logging.getLogger("bldfm.pbl_model")
+
+KAPPA = 0.4  # von Karman constant (pbl_model.py:61)
+
+_CLOSURES = ("MOST", "CONSTANT", "MOSTM", "OAAHOC")
+
+
+def _bad_closure(closure):
+    return ValueError(
+        f"Invalid closure type: {closure}. "
+        "Supported closures are 'MOST', 'CONSTANT', and 'OAAHOC'."
+    )
+
+
+def psi(x):
+    """Integrated Businger-Dyer stability correction for momentum (pbl_model.py:207-230)."""
+    x = np.asarray(x, dtype=np.float64)
+    stable = x > 0.0
+    # (1-16x)^(1/4) through the complex power like the reference, real part taken
+    xi = np.where(stable, np.nan, np.power(1.0 - 16.0 * x, 0.25, dtype=complex).real)
+    unstable_val = (
+        -2.0 * np.log(0.5 * (1.0 + xi))
+        - np.log(0.5 * (1.0 + xi**2))
+        + 2.0 * np.arctan(xi)
+        - 0.5 * np.pi
+    )
+    return np.where(stable, 5.0 * x, unstable_val)
+
+
+def phi(x):
+    """Businger-Dyer stability function for the eddy diffusivity (pbl_model.py:233-250)."""
+    x = np.asarray(x, dtype=np.float64)
+    return np.where(x > 0.0, 1.0 + 5.0 * x, np.power(1.0 - 16.0 * x, -0.5, dtype=complex).real)
+
+
+def _surface_layer(closure, zm, absum, ustar, z0, mol, tke):
+    """Resolve (ustar, z0) and closure constants (pbl_model.py:66-101)."""
+    extra = {}
+    if closure in ("CONSTANT", "MOST", "MOSTM"):
+        if z0 is None:
+            z0 = zm * np.exp(-KAPPA * absum / ustar + psi(zm / mol))
+        elif ustar is None:
+            ustar = absum * KAPPA / (np.log(zm / z0) + psi(zm / mol))
+        else:
+            raise ValueError("Either z0 or ustar must be provided.")
+    elif closure == "OAAHOC":
+        cl, cm, ch = 0.845, 0.0856, 0.204
+        if tke is None:
+            logger.warning("No tke provided. Setting TKE to 1.0.")
+            tke = 1.0
+        tke = np.array(tke)[..., np.newaxis]
+        z0 = zm * np.exp(-cm * cl * absum * np.sqrt(tke) / ustar**2)
+        extra = dict(cl=cl, cm=cm, ch=ch, tke=tke)
+    else:
+        raise _bad_closure(closure)
+    return ustar, z0, extra
+
+
+def vertical_profiles(
+    n,
+    meas_height,
+    wind,
+    ustar=None,
+    z0=None,
+    mol=1e9,
+    prsc=1.0,
+    closure="MOST",
+    domain_height=None,
+    stretch=None,
+    z0_min=0.001,
+    z0_max=2.0,
+    tke=None,
+):
+    """Vertical grid and (u, v, Kx, Ky, Kz) profiles; see pbl_model.py:22-56 for the arguments.
+
+    Returns ``z, (u, v, Kx, Ky, Kz)`` with ``z[0] = z0``, ``z[n] = meas_height`` and the grid
+    continuing to ``domain_height`` (default ``2*meas_height``), exponentially stretched.
+    """
+    zm = meas_height
+    um, vm = wind
+    absum = np.sqrt(um**2 + vm**2)
+    ustar, z0, extra = _surface_layer(closure, zm, absum, ustar, z0, mol, tke)
+
+    h = 2.0 * meas_height if stretch is None else stretch            # pbl_model.py:105-108
+    zmx = 2.0 * meas_height if domain_height is None else domain_height
+
+    bb = zm / (np.exp(-z0 / h) - np.exp(-zm / h))                      # :115-116
+    aa = bb * np.exp(-z0 / h)
+    zetamx = aa - bb * np.exp(-zmx / h)
+    dzeta = zm / n
+    zeta = np.arange(0.0, np.squeeze(zetamx).item() + dzeta, dzeta)    # :127
+    z = -h * np.log(-(zeta - aa) / bb)                                 # :129
+
+    if closure == "CONSTANT":                                          # :132-138
+        Km = KAPPA * ustar * zm / prsc
+        u = um * np.ones(len(z))
+        v = vm * np.ones(len(z))
+        K = Km * np.ones(len(z))
+        Kx = Ky = Kz = K
+    elif closure in ("MOST", "MOSTM"):                                 # :140-164
+        absu = ustar / KAPPA * (np.log(z / z0) + psi(z / mol))
+        u = um / absum * absu
+        v = vm / absum * absu
+        K = KAPPA * ustar * z / phi(z / mol) / prsc
+        if closure == "MOST":
+            Kx = Ky = Kz = K
+        else:
+            Kx = K * v**2 / (u**2 + v**2)
+            Ky = K * u**2 / (u**2 + v**2)
+            Kz = K
+    else:  # OAAHOC                                                    # :166-176
+        cl, cm, ch, tk = extra["cl"], extra["cm"], extra["ch"], extra["tke"]
+        absu = ustar**2 / cm / cl / np.sqrt(tk) * np.log(z / z0)
+        u = um / absum * absu
+        v = vm / absum * absu
+        K = ch * cl * z * np.sqrt(tk)
+        Kx = Ky = Kz = K
+
+    if logger.isEnabledFor(logging.INFO):
+        logger.info("Stats from vertical_profiles")
+        logger.info("z0    = %.3f m", z[0])
+        logger.info("ustar = %.3f m s-1", ustar)
+        logger.info("umax  = %.3f m s-1, vmax = %.3f m s-1, Kzmax = %.3f m2 s-1",
+                    np.max(u), np.max(v), np.max(Kz))
+    return z, (u, v, Kx, Ky, Kz)

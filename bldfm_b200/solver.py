@@ -1,0 +1,169 @@
+"""Drop-in host mirror of ``bldfm.solver`` (src/bldfm/solver.py) on top of libbldfm_b200.
+
+``steady_state_transport_solver`` keeps the reference signature, argument meaning, error messages,
+output shapes/dtypes and cache behaviour (solver.py:16-304); the body between the argument checks
+and the grid construction is ONE call into the CUDA library.  There is no CPU fallback.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import logging
+
+import numpy as np
+
+from . import _lib
+from . import config
+from .fft_manager import get_fft_manager
+
+logger = logging.getLogger("bldfm.solver")
+
+
+def _flags(footprint, analytic, precision):
+    if precision == "double":
+        f = _lib.DOUBLE
+    elif precision == "single":
+        f = 0
+    else:                                                                  # solver.py:187-188
+        raise ValueError("precision must be single (default) or double.")
+    if footprint:
+        f |= _lib.FOOTPRINT
+    if analytic:
+        f |= _lib.ANALYTIC
+    if config.MARCH_MODE == "fma":
+        f |= _lib.MARCH_FMA
+    elif config.MARCH_MODE != "exact":
+        raise ValueError("bldfm_b200.config.MARCH_MODE must be 'exact' or 'fma'")
+    if config.FFT_LIBRARY:
+        f |= _lib.FFT_LIBRARY
+    return f
+
+
+def _levels_array(levels):
+    lv = np.array([levels]) if np.ndim(levels) == 0 else np.asarray(levels)   # solver.py:102-103
+    return lv, np.ascontiguousarray(lv, dtype=np.int64)
+
+
+def make_grid(z, lv, domain, nx, ny):
+    """(X, Y, Z) of solver.py:293-298.  Values/shapes as the reference; see config.GRID_COPY."""
+    xmx, ymx = domain
+    x = np.linspace(0, xmx, nx, endpoint=False)
+    y = np.linspace(0, ymx, ny, endpoint=False)
+    zl = np.asarray(z)[lv]
+    if config.GRID_COPY:
+        Z, Y, X = np.meshgrid(zl, y, x, indexing="ij")
+    else:
+        shape = (len(zl), ny, nx)
+        Z = np.broadcast_to(zl[:, None, None], shape)
+        Y = np.broadcast_to(y[None, :, None], shape)
+        X = np.broadcast_to(x[None, None, :], shape)
+    return np.squeeze(X), np.squeeze(Y), np.squeeze(Z)
+
+
+def steady_state_transport_solver(
+    srf_flx,
+    z,
+    profiles,
+    domain,
+    levels,
+    modes=(512, 512),
+    meas_pt=(0.0, 0.0),
+    srf_bg_conc=0.0,
+    footprint=False,
+    analytic=False,
+    halo=None,
+    precision="single",
+    cache=None,
+):
+    """Steady-state advection-diffusion solve on the GPU; see solver.py:31-74 for the arguments.
+
+    Returns ``((X, Y, Z), conc, flx)`` exactly as the reference does (np.squeeze'd; float32 fields
+    only for precision="single" without a phase shift, float64 otherwise).
+    """
+    if cache is not None and footprint:                                    # solver.py:77-80
+        cached = cache.get(z, profiles, domain, modes, meas_pt, halo, precision)
+        if cached is not None:
+            return cached
+
+    q0 = np.asarray(srf_flx)
+    if q0.ndim != 2:
+        raise ValueError("srf_flx must be a 2D array")
+    ny, nx = q0.shape
+    geom = _lib.geometry(q0.shape, domain, modes, halo)                    # raises for odd modes (:90-91)
+    if geom.clamped:                                                       # solver.py:122-127
+        logger.info("Warning: Number of Fourier modes must not exeed number of grid cells.")
+        logger.info("Setting both equal.")
+    flags = _flags(footprint, analytic, precision)
+    lv, lv64 = _levels_array(levels)
+    nlv = len(lv64)
+
+    prob, keep = _lib.make_problem(z, profiles, meas_pt, srf_bg_conc)
+    f32 = bool(_lib.lib().bldfm_output_is_f32(flags, prob.xm, prob.ym))
+    dt = np.float32 if f32 else np.float64
+    conc = np.empty((nlv, ny, nx), dtype=dt)
+    flx = np.empty((nlv, ny, nx), dtype=dt)
+    src = None
+    if not footprint:
+        src = _lib.as_f64(q0)
+
+    plan = get_fft_manager().plan(geom)
+    rc = _lib.lib().bldfm_solve(
+        plan, C.byref(prob), lv64.ctypes.data_as(C.POINTER(C.c_int64)), nlv,
+        None if src is None else _lib.ptr(src), flags, _lib.ptr(conc), _lib.ptr(flx))
+    _lib.check(rc)
+    del keep
+
+    grid = make_grid(z, lv, domain, nx, ny)
+    result = (grid, np.squeeze(conc), np.squeeze(flx))
+
+    if cache is not None and footprint:                                    # solver.py:301-302
+        cache.put(z, profiles, domain, modes, meas_pt, halo, precision, *result)
+    return result
+
+
+def spectral_fields(srf_flx, z, profiles, domain, levels, modes=(512, 512), meas_pt=(0.0, 0.0),
+                    srf_bg_conc=0.0, footprint=False, analytic=False, halo=None,
+                    precision="single"):
+    """Parity hook: the combined, phase-shifted spectra (tfftp, tfftq) [nlv, nly, nlx] complex128
+    as they stand before solver.py:265."""
+    q0 = np.asarray(srf_flx)
+    geom = _lib.geometry(q0.shape, domain, modes, halo)
+    flags = _flags(footprint, analytic, precision)
+    _, lv64 = _levels_array(levels)
+    nlv = len(lv64)
+    prob, keep = _lib.make_problem(z, profiles, meas_pt, srf_bg_conc)
+    tp = np.empty((nlv, geom.nly, geom.nlx), dtype=np.complex128)
+    tq = np.empty((nlv, geom.nly, geom.nlx), dtype=np.complex128)
+    src = None if footprint else _lib.as_f64(q0)
+    plan = get_fft_manager().plan(geom)
+    _lib.check(_lib.lib().bldfm_solve_spectral(
+        plan, C.byref(prob), lv64.ctypes.data_as(C.POINTER(C.c_int64)), nlv,
+        None if src is None else _lib.ptr(src), flags, _lib.ptr(tp), _lib.ptr(tq)))
+    del keep
+    return tp, tq
+
+
+def ivp_solver(fftpq, profiles, z, levels, Lx, Ly):
+    """``ivp_solver`` of solver.py:307-374 on the GPU: returns (fftp_top, fftq_top, fftp, fftq)."""
+    p0 = np.ascontiguousarray(fftpq[0], dtype=np.complex128).ravel()
+    q0 = np.ascontiguousarray(fftpq[1], dtype=np.complex128).ravel()
+    Lx = _lib.as_f64(Lx).ravel()
+    Ly = _lib.as_f64(Ly).ravel()
+    M = p0.shape[0]
+    if not (q0.shape[0] == Lx.shape[0] == Ly.shape[0] == M):
+        raise ValueError("fftpq, Lx and Ly must have the same number of modes")
+    z = _lib.as_f64(z)
+    u, v, Kx, Ky, Kz = (_lib.as_f64(a) for a in profiles)
+    _, lv64 = _levels_array(levels)
+    nlv = len(lv64)
+    p_top = np.empty(M, np.complex128)
+    q_top = np.empty(M, np.complex128)
+    P = np.zeros((nlv, M), np.complex128)
+    Q = np.zeros((nlv, M), np.complex128)
+    flags = _lib.MARCH_FMA if config.MARCH_MODE == "fma" else 0
+    _lib.check(_lib.lib().bldfm_march(
+        config.DEVICE, M, _lib.ptr(p0), _lib.ptr(q0), len(z), _lib.ptr(z), _lib.ptr(u),
+        _lib.ptr(v), _lib.ptr(Kx), _lib.ptr(Ky), _lib.ptr(Kz), nlv,
+        lv64.ctypes.data_as(C.POINTER(C.c_int64)), _lib.ptr(Lx), _lib.ptr(Ly), flags,
+        _lib.ptr(p_top), _lib.ptr(q_top), _lib.ptr(P), _lib.ptr(Q)))
+    return p_top, q_top, P, Q

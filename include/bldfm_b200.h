@@ -1,0 +1,165 @@
+/*
+ * bldfm_b200.h -- C ABI of libbldfm_b200.so, the B200 (sm_100a) implementation of BLDFM's
+ * steady-state spectral advection-diffusion hot path.
+ *
+ * The reference (pure Python) has no FFI; the "binding" a maintainer adds is a ctypes stub that
+ * replaces the body of bldfm.solver.steady_state_transport_solver.  Each entry
+ * point below cites the reference interface it replaces (paths relative to /root/reference/).
+ *
+ * Conventions
+ *   - plain C types only; every function returns an int status (0 = BLDFM_OK, <0 = error) and never
+ *     throws; bldfm_last_error_string() gives the message for the calling thread's last error.
+ *   - complex arrays are interleaved (re,im) doubles == numpy complex128.
+ *   - "host" pointers are ordinary process memory; "device" pointers are CUDA device memory on the
+ *     plan's device.  Which one a buffer is, is stated per argument / selected by BLDFM_*_ON_DEVICE.
+ *   - a plan is not thread-safe; use one plan per host thread (the analogue of the reference's
+ *     per-process FFTManager singleton, src/bldfm/fft_manager.py:117-139).
+ */
+#ifndef BLDFM_B200_H
+#define BLDFM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLDFM_OK                    0
+#define BLDFM_ERR_ODD_MODES        -1  /* "modes must consist of even numbers."          src/bldfm/solver.py:90-91   */
+#define BLDFM_ERR_PRECISION        -2  /* "precision must be single (default) or double." src/bldfm/solver.py:187-188 */
+#define BLDFM_ERR_INVALID          -3  /* bad argument (message says which)                                          */
+#define BLDFM_ERR_CUDA             -4  /* CUDA runtime error (no device, launch failure, ...)                        */
+#define BLDFM_ERR_CUFFT            -5
+#define BLDFM_ERR_ALLOC            -6
+#define BLDFM_ERR_ODD_PAD          -7  /* (nxe-nlx) or (nye-nly) odd: src/bldfm/solver.py:130,142 mis-slices there    */
+#define BLDFM_ERR_ANALYTIC_LEVELS  -8  /* analytic=True broadcasts only for one level    src/bldfm/solver.py:197-202 */
+#define BLDFM_ERR_LEVEL_RANGE      -9  /* z[levels] would raise IndexError               src/bldfm/solver.py:296     */
+
+/* flags for bldfm_solve* (bit-or) */
+#define BLDFM_FOOTPRINT        0x001  /* footprint=True                                  src/bldfm/solver.py:25  */
+#define BLDFM_ANALYTIC         0x002  /* analytic=True                                   src/bldfm/solver.py:26  */
+#define BLDFM_DOUBLE           0x004  /* precision="double" (absent: "single")           src/bldfm/solver.py:28  */
+#define BLDFM_MARCH_FMA        0x008  /* opt-in: FMA-contracted march (faster, not bit-mirrored)                 */
+#define BLDFM_SRC_ON_DEVICE    0x010  /* srf_flx is a device pointer                                              */
+#define BLDFM_OUT_ON_DEVICE    0x020  /* conc/flx are device pointers                                             */
+#define BLDFM_ASYNC            0x040  /* with BLDFM_OUT_ON_DEVICE: enqueue on the plan's stream, do not sync      */
+#define BLDFM_FFT_LIBRARY      0x080  /* force the cuFFT transform path instead of the pruned in-house kernels    */
+
+typedef struct bldfm_plan bldfm_plan;
+
+/* Grid bookkeeping of steady_state_transport_solver (src/bldfm/solver.py:93-130). */
+typedef struct bldfm_geometry {
+    int32_t nx, ny;      /* srf_flx.shape == (ny, nx)                                   :94      */
+    int32_t px, py;      /* int(halo/dx), int(halo/dy)                                  :112-113 */
+    int32_t nxe, nye;    /* padded grid nx+2px, ny+2py                                  :119-120 */
+    int32_t nlx, nly;    /* retained modes AFTER the clamp (both set to nxe,nye)        :122-127 */
+    int32_t nfx, nfy;    /* size of the back-transform: nl + 2*((ne-nl)//2)             :130,269-278 */
+    int32_t clamped;     /* 1 if the clamp of :122-127 fired (caller logs the warning)           */
+    int32_t reserved;
+    double  dx, dy;      /* xmax/nx, ymax/ny                                            :98      */
+    double  halo;        /* resolved halo [m] (max(xmax,ymax) when None)                :108-109 */
+    double  xmax, ymax;
+} bldfm_geometry;
+
+/* One met/tower condition: the (z, profiles, meas_pt, srf_bg_conc) arguments of
+ * steady_state_transport_solver (src/bldfm/solver.py:16-30).  All arrays are HOST, length nz. */
+typedef struct bldfm_problem {
+    const double *z;
+    const double *u, *v, *Kx, *Ky, *Kz;
+    int32_t nz;
+    int32_t reserved;
+    double  xm, ym;          /* meas_pt     */
+    double  srf_bg_conc;     /* srf_bg_conc */
+} bldfm_problem;
+
+/* Timings of the most recent solve on a plan, CUDA-event measured on the plan's stream [ms]. */
+typedef struct bldfm_timings {
+    double forward_ms;   /* K1-K3  pad + forward transform (0 in footprint mode) */
+    double march_ms;     /* K4-K8  fused vertical march kernel                   */
+    double inverse_ms;   /* K9-K11 untruncate + back-transform + crop            */
+    double total_ms;     /* first kernel -> last kernel / copy                   */
+} bldfm_timings;
+
+/* ---- library ---------------------------------------------------------------------------------- */
+const char *bldfm_version(void);
+const char *bldfm_last_error_string(void);
+int  bldfm_device_count(int *count);
+
+/* Geometry (pure host arithmetic, usable without a GPU).  halo_is_none != 0 means halo=None.
+ * Returns BLDFM_ERR_ODD_MODES for odd modes.                              src/bldfm/solver.py:85-130 */
+int  bldfm_geometry_init(int32_t nx, int32_t ny, double xmax, double ymax, int32_t nlx, int32_t nly,
+                         int32_t halo_is_none, double halo, bldfm_geometry *out);
+
+/* Truncated wavenumber tables lx[nlx], ly[nly] (host arithmetic, bitwise equal to the numpy
+ * expressions of src/bldfm/solver.py:148-153). */
+int  bldfm_wavenumbers(const bldfm_geometry *g, double *lx, double *ly);
+
+/* 1 if the reference would return float32 fields for these arguments (precision="single", no phase
+ * shift applied: src/bldfm/solver.py:177-180,254-262 and SURVEY.md A.4), else 0 (float64). */
+int  bldfm_output_is_f32(int flags, double xm, double ym);
+
+/* ---- plan: device state reused across solves (cuFFT plans, workspaces, staged tables).
+ * Replaces FFTManager / get_fft_manager / reset_fft_manager (src/bldfm/fft_manager.py:12-145) and the
+ * numba JIT cache behind @parallelize (src/bldfm/utils.py:95-106). */
+int  bldfm_plan_create(const bldfm_geometry *g, int device, bldfm_plan **out);
+int  bldfm_plan_destroy(bldfm_plan *plan);
+/* cudaStream_t of the plan as an opaque pointer (for event timing / stream interop by the caller) */
+void *bldfm_plan_stream(bldfm_plan *plan);
+int  bldfm_plan_synchronize(bldfm_plan *plan);
+/* number of this library's own kernels launched on the plan so far */
+int64_t bldfm_plan_launch_count(const bldfm_plan *plan);
+/* enable (1) / disable (0) per-stage event timing; read the last solve's numbers (synchronises) */
+int  bldfm_plan_set_profiling(bldfm_plan *plan, int enabled);
+int  bldfm_plan_last_timings(bldfm_plan *plan, bldfm_timings *out);
+/* bytes of device workspace currently held by the plan */
+int64_t bldfm_plan_workspace_bytes(const bldfm_plan *plan);
+
+/* ---- the hot path.  Replaces the body of steady_state_transport_solver (src/bldfm/solver.py:82-290):
+ * pad/FFT/truncate, two ivp_solver marches, shooting combine, (0,0) mode, phase shift, untruncate,
+ * back-transform and crop.  Grid construction (:293-298) and the disk cache (:77-80,301-302) stay on
+ * the Python side.
+ *   levels[nlv]  level indices; rows are filled in visit order like the reference (:352-355).
+ *   srf_flx      [ny][nx] float64 (ignored and may be NULL with BLDFM_FOOTPRINT).
+ *   conc, flx    [nlv][ny][nx]; float64, or float32 when bldfm_output_is_f32(). */
+int  bldfm_solve(bldfm_plan *plan, const bldfm_problem *prob, const int64_t *levels, int32_t nlv,
+                 const double *srf_flx, int flags, void *conc, void *flx);
+
+/* Many (tower, met) conditions in one launch.  Replaces the loops / process pool of
+ * run_bldfm_timeseries/_multitower/_parallel (src/bldfm/interface.py:141-326).  Problems whose
+ * (z, profiles, srf_bg_conc) are byte-identical share one march (towers differ only by the phase
+ * shift).  All problems share geometry, levels, flags and srf_flx.
+ *   conc, flx    [nprob][nlv][ny][nx]. */
+int  bldfm_solve_batched(bldfm_plan *plan, int32_t nprob, const bldfm_problem *probs,
+                         const int64_t *levels, int32_t nlv, const double *srf_flx, int flags,
+                         void *conc, void *flx);
+
+/* Spectral-stage export for parity tests: the combined, phase-shifted spectra tfftp/tfftq
+ * [nlv][nly][nlx] complex128 (host) as they stand before src/bldfm/solver.py:265. */
+int  bldfm_solve_spectral(bldfm_plan *plan, const bldfm_problem *prob, const int64_t *levels,
+                          int32_t nlv, const double *srf_flx, int flags, double *tfftp, double *tfftq);
+
+/* ivp_solver itself (src/bldfm/solver.py:307-374) for isolated parity tests: host arrays,
+ * p0,q0,Lx,Ly [M]; outputs p_top,q_top [M] and P,Q [nlv][M] (complex128). */
+int  bldfm_march(int device, int64_t M, const double *p0, const double *q0, int32_t nz,
+                 const double *z, const double *u, const double *v, const double *Kx,
+                 const double *Ky, const double *Kz, int32_t nlv, const int64_t *levels,
+                 const double *Lx, const double *Ly, int flags,
+                 double *p_top, double *q_top, double *P, double *Q);
+
+/* ---- memory helpers (so that callers need no other CUDA binding) */
+int  bldfm_host_alloc(int64_t bytes, void **out);      /* pinned host memory */
+int  bldfm_host_free(void *p);
+int  bldfm_device_alloc(int device, int64_t bytes, void **out);
+int  bldfm_device_free(int device, void *p);
+int  bldfm_memcpy_d2h(int device, void *dst_host, const void *src_dev, int64_t bytes);
+int  bldfm_memcpy_h2d(int device, void *dst_dev, const void *src_host, int64_t bytes);
+
+/* FP64 pipe micro-benchmark used for the roofline denominator: runs `iters` dependent-chain
+ * DFMA (fma != 0) or DMUL/DADD (fma == 0) operations per thread on a full grid and returns the
+ * achieved rate in G(FMA-or-op)/s.  One FMA counts as ONE here; callers multiply by 2 for flops. */
+int  bldfm_fp64_peak(int device, int fma, int iters, double *gops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BLDFM_B200_H */

@@ -1,0 +1,84 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports everything include/*.h declares,
+its pure-host helpers match numpy bit for bit, and compute calls fail loudly without a GPU."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def L():
+    from bldfm_b200 import build, _lib
+    build.build()
+    return _lib
+
+
+def test_header_and_library_export_the_same_symbols(L):
+    header = (ROOT / "include" / "bldfm_b200.h").read_text()
+    declared = set(re.findall(r"\b(bldfm_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(L.EXPORTS)
+    lib = L.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.bldfm_version()
+
+
+def test_geometry_matches_reference_bookkeeping(L, oracle):
+    cases = [((512, 512), (4000.0, 4000.0), (512, 512), None),
+             ((128, 64), (100.0, 700.0), (64, 128), None),
+             ((48, 64), (500.0, 375.0), (48, 32), 200.0),
+             ((9, 11), (220.0, 180.0), (512, 512), 45.0),
+             ((256, 512), (2000.0, 1000.0), (512, 512), None),
+             ((40, 48), (960.0, 800.0), (24, 16), 0.0)]
+    for shape, domain, modes, halo in cases:
+        g = L.geometry(shape, domain, modes, halo)
+        o = oracle.geometry(shape, domain, modes, halo)
+        for k in ("nx", "ny", "px", "py", "nxe", "nye", "nlx", "nly", "nfx", "nfy"):
+            assert getattr(g, k) == o[k], (k, shape, modes)
+        assert g.dx == o["dx"] and g.dy == o["dy"] and g.halo == o["halo"]
+        lx = np.empty(g.nlx)
+        ly = np.empty(g.nly)
+        assert L.lib().bldfm_wavenumbers(C.byref(g), L.dptr(lx), L.dptr(ly)) == 0
+        olx, oly = oracle.wavenumbers(o)
+        assert np.array_equal(lx, olx) and np.array_equal(ly, oly)
+
+
+def test_error_mapping_without_gpu(L):
+    from bldfm_b200 import steady_state_transport_solver
+    z = np.linspace(0.1, 20.0, 10)
+    prof = (z, z, z, z, z)
+    with pytest.raises(ValueError, match="modes must consist of even numbers."):
+        steady_state_transport_solver(np.zeros((8, 8)), z, prof, (10.0, 10.0), 3, modes=(7, 8))
+    with pytest.raises(ValueError, match="precision must be single \\(default\\) or double."):
+        steady_state_transport_solver(np.zeros((8, 8)), z, prof, (10.0, 10.0), 3, modes=(8, 8),
+                                      precision="half")
+    assert L.lib().bldfm_output_is_f32(0, 0.0, 0.0) == 1
+    assert L.lib().bldfm_output_is_f32(0, 1.0, 0.0) == 0
+    assert L.lib().bldfm_output_is_f32(L.DOUBLE, 0.0, 0.0) == 0
+    assert L.lib().bldfm_output_is_f32(L.FOOTPRINT, 0.0, 0.0) == 0
+
+
+def test_no_cpu_fallback(L):
+    """Without a CUDA device the product must raise, never compute on the host."""
+    if L.device_count() > 0:
+        pytest.skip("a GPU is present")
+    from bldfm_b200 import steady_state_transport_solver, ivp_solver
+    z = np.linspace(0.1, 20.0, 10)
+    prof = (z, z, z, z, z)
+    with pytest.raises(L.BldfmError, match="no CUDA device"):
+        steady_state_transport_solver(np.zeros((8, 8)), z, prof, (10.0, 10.0), 3, modes=(8, 8),
+                                      footprint=True)
+    with pytest.raises(L.BldfmError, match="no CUDA device"):
+        ivp_solver((np.ones(4, complex), np.zeros(4, complex)), prof, z, [3], np.ones(4), np.ones(4))
+
+
+def test_product_never_imports_oracle():
+    pkg = ROOT / "bldfm_b200"
+    for f in pkg.rglob("*.py"):
+        assert "oracle" not in f.read_text(), f
+    for f in list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
+        assert "oracle" not in f.read_text(), f

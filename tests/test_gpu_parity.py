@@ -1,0 +1,217 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden vectors.
+
+Tolerances (north_star): rel-L2 <= 1e-10 in FP64, <= 1e-5 in the FP32-storage mode; the march
+itself (ivp_solver) is compared BITWISE.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, SOLVE_CASES, load_case, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_F64 = 1e-10
+TOL_F32 = 1e-5
+
+
+@pytest.fixture(scope="module")
+def B(gpu_lib):
+    import bldfm_b200
+    return bldfm_b200
+
+
+def test_ivp_bitwise_against_reference_golden(B):
+    d = np.load(GOLDEN / "ivp.npz")
+    profs = (d["u"], d["v"], d["Kx"], d["Ky"], d["Kz"])
+    for tag in ("a", "b"):
+        pt, qt, P, Q = B.ivp_solver((d[f"{tag}_p0"], d[f"{tag}_q0"]), profs, d["z"], d["levels"],
+                                    d["Lx"], d["Ly"])
+        assert np.array_equal(pt, d[f"{tag}_ptop"])
+        assert np.array_equal(qt, d[f"{tag}_qtop"])
+        assert np.array_equal(P, d[f"{tag}_P"])
+        assert np.array_equal(Q, d[f"{tag}_Q"])
+
+
+def test_ivp_bitwise_against_oracle_random(B, oracle):
+    from bldfm_b200.pbl_model import vertical_profiles
+    rng = np.random.default_rng(7)
+    z, profs = vertical_profiles(128, 10.0, (2.0, -5.0), ustar=0.35, mol=-30.0)
+    M = 5000
+    Lx = rng.uniform(-0.2, 0.2, M)
+    Ly = rng.uniform(-0.2, 0.2, M)
+    p0 = rng.normal(size=M) + 1j * rng.normal(size=M)
+    q0 = rng.normal(size=M) + 1j * rng.normal(size=M)
+    lv = np.array([0, 3, 128, len(z) - 1])
+    got = B.ivp_solver((p0, q0), profs, z, lv, Lx, Ly)
+    ref = oracle.ivp((p0, q0), profs, z, lv, Lx, Ly, nthreads=4)
+    for g, r in zip(got, ref):
+        assert np.array_equal(g, r)
+
+
+def test_ivp_fma_mode_is_close_but_optional(B, oracle):
+    d = np.load(GOLDEN / "ivp.npz")
+    profs = (d["u"], d["v"], d["Kx"], d["Ky"], d["Kz"])
+    B.config.MARCH_MODE = "fma"
+    try:
+        pt, qt, P, Q = B.ivp_solver((d["a_p0"], d["a_q0"]), profs, d["z"], d["levels"], d["Lx"], d["Ly"])
+    finally:
+        B.config.MARCH_MODE = "exact"
+    assert rel_l2(np.abs(pt), np.abs(d["a_ptop"])) < 1e-12
+    assert rel_l2(np.abs(P), np.abs(d["a_P"])) < 1e-12
+
+
+@pytest.mark.parametrize("name", SOLVE_CASES)
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_spectral_stage_against_oracle(B, oracle, name, precision):
+    from bldfm_b200.solver import spectral_fields
+    kw, _ = load_case(name)
+    tp, tq = spectral_fields(precision=precision, **kw)
+    otp, otq = oracle.solve(precision=precision, return_spectral=True, **kw)
+    tol = 1e-12 if precision == "double" else 2e-7
+    assert tp.shape == otp.shape
+    assert rel_l2(np.abs(tp - otp), np.abs(otp)) <= tol
+    assert rel_l2(np.abs(tq - otq), np.abs(otq)) <= tol
+
+
+@pytest.mark.parametrize("library_fft", [False, True])
+@pytest.mark.parametrize("name", SOLVE_CASES)
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_solve_against_reference_golden(B, name, precision, library_fft):
+    kw, d = load_case(name)
+    B.config.FFT_LIBRARY = library_fft
+    try:
+        grid, conc, flx = B.steady_state_transport_solver(precision=precision, **kw)
+    finally:
+        B.config.FFT_LIBRARY = False
+    ref_c, ref_f = d[f"conc_{precision}"], d[f"flx_{precision}"]
+    assert conc.shape == ref_c.shape and flx.shape == ref_f.shape
+    assert conc.dtype == ref_c.dtype and flx.dtype == ref_f.dtype
+    if ref_c.dtype == np.float32 or precision == "single":
+        tol = TOL_F32
+    else:
+        tol = TOL_F64
+    assert rel_l2(conc, ref_c) <= tol, rel_l2(conc, ref_c)
+    assert rel_l2(flx, ref_f) <= tol, rel_l2(flx, ref_f)
+    for got, key in zip(grid, ("X", "Y", "Z")):
+        assert got.shape == d[key].shape
+        assert np.array_equal(got, d[key])
+
+
+def test_reference_regression_goldens(B):
+    """The reference's own tests/references goldens with its own tolerances (test_regression.py:18-24)."""
+    ref = np.load(GOLDEN / "refgold.npz")
+    for name in ("source_area", "plume_3d"):
+        kw, _ = load_case(name)
+        _, conc, flx = B.steady_state_transport_solver(precision="single", **kw)
+        np.testing.assert_allclose(conc, ref[f"{name}_conc"], atol=1e-6, rtol=1e-5)
+        np.testing.assert_allclose(flx, ref[f"{name}_flx"], atol=1e-6, rtol=1e-5)
+
+
+def _config2(n=512):
+    from bldfm_b200.pbl_model import vertical_profiles
+    z, profs = vertical_profiles(64, 10.0, (-3.0, -4.0), ustar=0.4, mol=-50.0)
+    return dict(srf_flx=np.zeros((n, n)), z=z, profiles=profs, domain=(4000.0, 4000.0), levels=64,
+                modes=(n, n), meas_pt=(2000.0, 2000.0), footprint=True, precision="double")
+
+
+def test_baseline_config2_full_size_against_oracle(B, oracle):
+    """BASELINE config 2 (512x512x64 FP64 unstable footprint) at full size: rel-L2 <= 1e-10."""
+    kw = _config2()
+    _, conc, flx = B.steady_state_transport_solver(**kw)
+    _, oc, of = oracle.solve(nthreads=oracle.max_threads(), **kw)
+    assert rel_l2(conc, oc) <= TOL_F64, rel_l2(conc, oc)
+    assert rel_l2(flx, of) <= TOL_F64, rel_l2(flx, of)
+    # size-independent properties: footprint weights sum to ~1 over the domain, finite, mostly positive
+    assert np.isfinite(flx).all() and np.isfinite(conc).all()
+    assert 0.25 < flx.sum() <= 1.05
+    assert flx.min() >= -1e-4 * flx.max()
+
+
+def test_config2_fma_mode_within_tolerance(B, oracle):
+    kw = _config2(256)
+    kw["domain"] = (2000.0, 2000.0)
+    kw["meas_pt"] = (1000.0, 1000.0)
+    B.config.MARCH_MODE = "fma"
+    try:
+        _, conc, flx = B.steady_state_transport_solver(**kw)
+    finally:
+        B.config.MARCH_MODE = "exact"
+    _, oc, of = oracle.solve(nthreads=oracle.max_threads(), **kw)
+    assert rel_l2(conc, oc) <= TOL_F64
+    assert rel_l2(flx, of) <= TOL_F64
+
+
+def test_linearity_in_source(B):
+    """Non-footprint solves are linear in srf_flx (size-independent property)."""
+    from bldfm_b200.pbl_model import vertical_profiles
+    from bldfm_b200.utils import ideal_source
+    z, profs = vertical_profiles(16, 10.0, (5.0, 1.0), ustar=0.4)
+    dom = (1600.0, 800.0)
+    a = ideal_source((128, 64), dom, shape="diamond")
+    b = ideal_source((128, 64), dom, src_loc=(300.0, 500.0), shape="point")
+    kw = dict(z=z, profiles=profs, domain=dom, levels=[4, 16], modes=(128, 64), meas_pt=(800.0, 400.0),
+              precision="double")
+    _, ca, fa = B.steady_state_transport_solver(a, **kw)
+    _, cb, fb = B.steady_state_transport_solver(b, **kw)
+    _, cs, fs = B.steady_state_transport_solver(2.0 * a - 3.0 * b, **kw)
+    assert rel_l2(cs, 2.0 * ca - 3.0 * cb) < 1e-12
+    assert rel_l2(fs, 2.0 * fa - 3.0 * fb) < 1e-12
+
+
+def test_footprint_convolution_equals_dispersion(B):
+    """Green's-function identity: flux at the tower from a dispersion solve equals
+    sum(footprint * source) (what point_measurement computes, utils.py:80-92)."""
+    from bldfm_b200.pbl_model import vertical_profiles
+    from bldfm_b200.utils import ideal_source, point_measurement
+    z, profs = vertical_profiles(16, 10.0, (4.0, 2.0), ustar=0.4, mol=-100.0)
+    dom = (1280.0, 1280.0)
+    n = 128
+    src = ideal_source((n, n), dom, src_loc=(400.0, 500.0), shape="circle")
+    tower = (800.0, 800.0)   # on a grid node: 800/10
+    kw = dict(z=z, profiles=profs, domain=dom, levels=16, modes=(n, n), precision="double")
+    _, _, fp = B.steady_state_transport_solver(np.zeros((n, n)), meas_pt=tower, footprint=True, **kw)
+    _, _, fl = B.steady_state_transport_solver(src, meas_pt=(0.0, 0.0), footprint=False, **kw)
+    ix, iy = int(round(tower[0] / (dom[0] / n))), int(round(tower[1] / (dom[1] / n)))
+    assert abs(point_measurement(fp, src) - fl[iy, ix]) <= 1e-9 * abs(fl[iy, ix])
+
+
+def test_scalar_vs_array_levels_and_dtypes(B):
+    kw, d = load_case("noshift")
+    g1, c1, f1 = B.steady_state_transport_solver(precision="single", **kw)
+    assert c1.dtype == np.float32 and c1.ndim == 2
+    kw2 = dict(kw)
+    kw2["levels"] = [int(kw["levels"])]
+    g2, c2, f2 = B.steady_state_transport_solver(precision="single", **kw2)
+    assert np.array_equal(c1, c2) and c2.ndim == 2
+    kw3 = dict(kw)
+    kw3["levels"] = [2, 16]
+    g3, c3, f3 = B.steady_state_transport_solver(precision="double", **kw3)
+    assert c3.shape == (2,) + c1.shape and c3.dtype == np.float64
+    assert g3[2].shape == c3.shape
+
+
+def test_errors_and_clamp(B, caplog):
+    import logging
+    kw, d = load_case("clamp")
+    with caplog.at_level(logging.INFO, logger="bldfm.solver"):
+        B.steady_state_transport_solver(precision="double", **kw)
+    assert any("Setting both equal." in r.message for r in caplog.records)
+    with pytest.raises(IndexError):
+        B.steady_state_transport_solver(precision="double", **{**kw, "levels": 999})
+    kw2, _ = load_case("analytic")
+    with pytest.raises(ValueError):
+        B.steady_state_transport_solver(**{**kw2, "levels": [3, 12]})
+
+
+def test_cache_roundtrip(B, tmp_path):
+    from bldfm_b200.cache import GreensFunctionCache
+    kw, d = load_case("source_area")
+    cache = GreensFunctionCache(cache_dir=tmp_path / "c")
+    r1 = B.steady_state_transport_solver(precision="double", cache=cache, **kw)
+    assert len(list((tmp_path / "c").glob("*.npz"))) == 1
+    r2 = B.steady_state_transport_solver(precision="double", cache=cache, **kw)
+    assert np.array_equal(r1[1], r2[1]) and np.array_equal(r1[2], r2[2])
+    for a, b in zip(r1[0], r2[0]):
+        assert np.array_equal(a, b)

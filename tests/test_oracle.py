@@ -1,0 +1,98 @@
+"""CPU tests: the oracle (oracle/) against golden vectors generated from the unmodified reference."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, SOLVE_CASES, load_case, rel_l2
+
+
+def test_ivp_bitwise_against_numba_golden(oracle):
+    d = np.load(GOLDEN / "ivp.npz")
+    profs = (d["u"], d["v"], d["Kx"], d["Ky"], d["Kz"])
+    for tag in ("a", "b"):
+        for nthreads in (1, 3):
+            pt, qt, P, Q = oracle.ivp((d[f"{tag}_p0"], d[f"{tag}_q0"]), profs, d["z"], d["levels"],
+                                      d["Lx"], d["Ly"], nthreads=nthreads)
+            assert np.array_equal(pt, d[f"{tag}_ptop"])
+            assert np.array_equal(qt, d[f"{tag}_qtop"])
+            assert np.array_equal(P, d[f"{tag}_P"])
+            assert np.array_equal(Q, d[f"{tag}_Q"])
+
+
+@pytest.mark.parametrize("name", SOLVE_CASES)
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_solve_matches_reference_golden(oracle, name, precision):
+    kw, d = load_case(name)
+    grid, conc, flx = oracle.solve(precision=precision, **kw)
+    ref_c, ref_f = d[f"conc_{precision}"], d[f"flx_{precision}"]
+    assert conc.shape == ref_c.shape and flx.shape == ref_f.shape
+    assert conc.dtype == ref_c.dtype and flx.dtype == ref_f.dtype
+    # same numpy/scipy build as the generator -> identical; allow last-digit FFT differences
+    tol = 1e-6 if ref_c.dtype == np.float32 else 1e-13
+    assert rel_l2(conc, ref_c) <= tol
+    assert rel_l2(flx, ref_f) <= tol
+    if precision == "double":
+        for got, key in zip(grid, ("X", "Y", "Z")):
+            assert np.array_equal(got, d[key])
+
+
+def test_reference_regression_goldens(oracle):
+    """The reference's own tests/references/{source_area,plume_3d}.npz (atol 1e-6, rtol 1e-5)."""
+    ref = np.load(GOLDEN / "refgold.npz")
+    for name in ("source_area", "plume_3d"):
+        kw, _ = load_case(name)
+        _, conc, flx = oracle.solve(precision="single", **kw)
+        np.testing.assert_allclose(conc, ref[f"{name}_conc"], atol=1e-6, rtol=1e-5)
+        np.testing.assert_allclose(flx, ref[f"{name}_flx"], atol=1e-6, rtol=1e-5)
+        assert rel_l2(flx, ref[f"{name}_flx"]) < 1e-12
+
+
+def test_reference_goldens_in_place(oracle):
+    """Same check straight from /root/reference when it is mounted (build container only)."""
+    refdir = Path("/root/reference/tests/references")
+    if not refdir.exists():
+        pytest.skip("reference tree not mounted")
+    for name in ("source_area", "plume_3d"):
+        ref = np.load(refdir / f"{name}.npz")
+        kw, _ = load_case(name)
+        _, conc, flx = oracle.solve(precision="single", **kw)
+        np.testing.assert_allclose(conc, ref["conc"], atol=1e-6, rtol=1e-5)
+        np.testing.assert_allclose(flx, ref["flx"], atol=1e-6, rtol=1e-5)
+
+
+def test_error_messages(oracle):
+    kw, _ = load_case("source_area")
+    with pytest.raises(ValueError, match="modes must consist of even numbers."):
+        oracle.solve(**{**kw, "modes": (63, 128)})
+    with pytest.raises(ValueError, match="precision must be single"):
+        oracle.solve(precision="half", **kw)
+
+
+def test_footprint_sums_to_one(oracle):
+    """Sum of the flux footprint over the padded domain is 1 by construction;
+    over the cropped domain it lies in (0.25, 1.05] (reference tests/test_integration.py:295-399)."""
+    kw, _ = load_case("source_area")
+    _, conc, flx = oracle.solve(precision="double", **kw)
+    assert 0.25 < flx.sum() <= 1.05
+
+
+def test_profiles_bitwise():
+    from bldfm_b200.pbl_model import vertical_profiles
+    d = np.load(GOLDEN / "profiles.npz")
+    cases = json.loads(str(d["cases"]))
+    for i, c in enumerate(cases):
+        c["wind"] = tuple(c["wind"])
+        z, p = vertical_profiles(**c)
+        assert np.array_equal(z, d[f"z{i}"])
+        for name, a in zip(("u", "v", "Kx", "Ky", "Kz"), p):
+            assert np.array_equal(np.asarray(a, dtype=np.float64).reshape(-1), d[f"{name}{i}"])
+
+
+def test_profile_errors():
+    from bldfm_b200.pbl_model import vertical_profiles
+    with pytest.raises(ValueError, match="Either z0 or ustar"):
+        vertical_profiles(8, 10.0, (1.0, 0.0), ustar=0.3, z0=0.1)
+    with pytest.raises(ValueError, match="Invalid closure type"):
+        vertical_profiles(8, 10.0, (1.0, 0.0), ustar=0.3, closure="NOPE")
