@@ -22,6 +22,14 @@ def rel_l2(a, b):
     return float(np.linalg.norm((a - b).ravel()) / (nb if nb > 0 else 1.0))
 
 
+def rel_l2c(a, b):
+    """rel-L2 for complex arrays."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    nb = np.linalg.norm(b.ravel())
+    return float(np.linalg.norm((a - b).ravel()) / (nb if nb > 0 else 1.0))
+
+
 SOLVE_CASES = sorted(json.loads((GOLDEN / "index.json").read_text()).keys())
 
 
