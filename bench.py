@@ -153,7 +153,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="problems per launch for the extra batched figure")
@@ -258,9 +258,12 @@ def main():
     for _ in range(args.warmup):
         bldfm_b200.steady_state_transport_solver(**kw)
     barrier()
+    e2e_calls = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
+        tc = time.perf_counter()
         grid, conc, flx = bldfm_b200.steady_state_transport_solver(**kw)
+        e2e_calls.append(time.perf_counter() - tc)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     barrier()
@@ -320,6 +323,8 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(S * 128 + 64 + 24 + (S + 1) * 4),
                     "d2h_bytes_per_step": int(2 * 512 * 512 * 8),
+                    "ms_per_step_median_rank0": float(np.median(e2e_calls)) * 1e3,
+                    "ms_per_step_max_rank0": float(np.max(e2e_calls)) * 1e3,
                     "api": "bldfm_b200.steady_state_transport_solver (numpy in/out)"},
             "gpu_launches": launches,
             "clocks": clocks.summary(),

@@ -104,6 +104,7 @@ struct bldfm_plan {
     size_t pad_state_elem = 0, pad_state_fields = 0;   // what the static zeros of pad_in match
     DevBuf src_in, src_pad;  // non-footprint: device copy of srf_flx, padded complex / spectrum
     DevBuf fft_work;         // pruned path: intermediate [field][nly][nx]
+    DevBuf tw64, tw32;       // pruned path: twiddle tables  x[nfx] | y[nfy]  (double2 / float2)
     DevBuf out_c, out_f;     // device outputs when the caller wants host results
     Staging staging[kStagingSlots];
     int staging_next = 0;
@@ -266,6 +267,29 @@ int build_levels(const int64_t* levels, int nlv, int nz_min, int nz_max, LevelPl
         }
     }
     lp.visited = row;
+    return BLDFM_OK;
+}
+
+int ensure_twiddles(bldfm_plan* pl, bool f32, PrunedFftTables* tab)
+{
+    const bldfm_geometry& g = pl->g;
+    DevBuf& buf = f32 ? pl->tw32 : pl->tw64;
+    const size_t esz = f32 ? sizeof(float2) : sizeof(double2);
+    if (!buf.p) {
+        std::vector<double> tx, ty;
+        fft_twiddles(g.nfx, tx);
+        fft_twiddles(g.nfy, ty);
+        tx.insert(tx.end(), ty.begin(), ty.end());
+        TRY(buf.ensure(((size_t)g.nfx + g.nfy) * esz));
+        if (f32) {
+            std::vector<float> tf(tx.begin(), tx.end());
+            CUDA_TRY(cudaMemcpy(buf.p, tf.data(), tf.size() * sizeof(float), cudaMemcpyHostToDevice));
+        } else {
+            CUDA_TRY(cudaMemcpy(buf.p, tx.data(), tx.size() * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
+    tab->tw_x = buf.p;
+    tab->tw_y = static_cast<const char*>(buf.p) + (size_t)g.nfx * esz;
     return BLDFM_OK;
 }
 
@@ -505,7 +529,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         d_conc = pl->out_c.p; d_flx = pl->out_f.p;
     }
     const bool forward_dir = footprint;   // fft2(norm="backward") vs ifft2(norm="forward")  solver.py:280-287
-    const bool use_library = (flags & BLDFM_FFT_LIBRARY) || !pruned_fft_supported(g, spec_f32);
+    const bool use_library = (flags & BLDFM_FFT_LIBRARY) || !pruned_fft_supported(g, spec_f32, pl->smem_optin);
     if (use_library) {
         const size_t field_bytes = (size_t)g.nfx * g.nfy * celem;
         int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nfields, pl->pad_budget / field_bytes));
@@ -555,9 +579,15 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         }
     } else {
         int nl = 0;
+        PrunedFftTables tab;
+        TRY(ensure_twiddles(pl, spec_f32, &tab));
         TRY(pl->fft_work.ensure(pruned_fft_work_bytes(g, spec_f32, nfields)));
-        TRY(pruned_fft_run(pl->stream, pl->num_sms, pl->smem_optin, g, spec_f32, forward_dir,
-                           pl->spec_p.p, pl->spec_q.p, nfields, pl->fft_work.p, d_conc, d_flx, &nl));
+        cudaError_t fe = spec_f32
+            ? pruned_fft_launch<float>(pl->stream, pl->smem_optin, g, forward_dir, pl->spec_p.p, pl->spec_q.p,
+                                       nfields, pl->fft_work.p, d_conc, d_flx, tab, &nl)
+            : pruned_fft_launch<double>(pl->stream, pl->smem_optin, g, forward_dir, pl->spec_p.p, pl->spec_q.p,
+                                        nfields, pl->fft_work.p, d_conc, d_flx, tab, &nl);
+        if (fe != cudaSuccess) return fail(BLDFM_ERR_CUDA, std::string("pruned FFT launch: ") + cudaGetErrorString(fe));
         pl->launches += nl;
     }
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev[3], pl->stream));
@@ -716,7 +746,7 @@ int bldfm_plan_destroy(bldfm_plan* pl)
     for (auto& kv : pl->fft_plans) cufftDestroy(kv.second);
     pl->tables.release(); pl->params.release(); pl->spec_p.release(); pl->spec_q.release();
     pl->pad_in.release(); pl->pad_out.release(); pl->src_in.release(); pl->src_pad.release();
-    pl->fft_work.release(); pl->out_c.release(); pl->out_f.release();
+    pl->fft_work.release(); pl->tw64.release(); pl->tw32.release(); pl->out_c.release(); pl->out_f.release();
     for (auto& s : pl->staging) {
         if (s.host) cudaFreeHost(s.host);
         if (s.done) cudaEventDestroy(s.done);

@@ -1,20 +1,372 @@
-// fft.cuh -- pruned in-house back-transform (K9+K10+K11 fused).  Placeholder until the shared-memory
-// mixed-radix kernels land: reports "unsupported" so that api.cu takes the library (cuFFT) path.
+// fft.cuh -- pruned in-house horizontal back-transform (K9 + K10 + K11 fused) for sm_100a.
+//
+// The reference un-truncates the retained modes into the full padded spectrum, runs two complete
+// complex 2-D FFTs of size nfy x nfx per output level and then crops the real part
+// (src/bldfm/solver.py:265-290).  Only nly x nlx inputs are non-zero and only ny x nx outputs are
+// kept, so the work is done here as two batched 1-D passes that never materialise a padded array:
+//
+//   pass X  for each retained ky row : A[ky][x']  = sum_kx S[ky][kx] w_x^{fx (px + x')},  x' in [0,nx)
+//   pass Y  for each kept column x'  : out[y'][x'] = Re sum_ky A[ky][x'] w_y^{fy (py + y')}, y' in [0,ny)
+//
+// Each 1-D transform is a full length-N mixed-radix (2,3,4,5,8) decimation-in-time FFT held in
+// shared memory (in place, digit-reversed scatter on load, natural order on store) with zero-filled
+// inputs; the output window is the only thing written.  Several transforms share a CTA so that the
+// strided side of each pass still moves whole 32/64-byte segments.  Twiddles come from a per-plan
+// table exp(-2*pi*i*k/N) built on the host in extended precision.
 #pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
 
 #include "../../include/bldfm_b200.h"
 #include "common.cuh"
 
 namespace bldfm {
 
-inline bool pruned_fft_supported(const bldfm_geometry&, bool) { return false; }
+constexpr int kFftMaxStages = 12;
+constexpr int kFftThreads = 256;
+constexpr int kFftPad = 2;   // elements of padding between the transforms of one CTA
 
-inline size_t pruned_fft_work_bytes(const bldfm_geometry&, bool, int64_t) { return 0; }
+struct FftPassArgs {
+    int32_t N;                 // transform length
+    int32_t nstages;
+    int32_t radix[kFftMaxStages];
+    int32_t nl;                // non-zero inputs (fftfreq order: 0..(nl-1)/2, -(nl/2)..-1)
+    int32_t win0, nwin;        // output window [win0, win0+nwin)
+    int32_t cw;                // transforms per CTA
+    int32_t ntrans;            // transforms per field
+    int32_t t_fast;            // 1: consecutive threads walk the transform index first
+    int32_t conj_io;           // 1: inverse transform through conj(FFT(conj(x)))
+    int64_t in_field_stride, in_tstride, in_kstride;      // in elements
+    int64_t out_field_stride, out_tstride, out_jstride;   // in elements
+    int32_t nfields_first;     // fields [0, nfields_first) use in/out, the rest in2/out2
+    const void* in;
+    const void* in2;
+    void* out;
+    void* out2;
+    const void* twiddle;       // [N] complex of the compute type: exp(-2*pi*i*k/N)
+};
 
-inline int pruned_fft_run(cudaStream_t, int, size_t, const bldfm_geometry&, bool, bool, const void*,
-                          const void*, int64_t, void*, void*, void*, int*)
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
+template <typename T> __device__ __forceinline__ typename Vec2<T>::type mk2(T x, T y);
+template <> __device__ __forceinline__ double2 mk2<double>(double x, double y) { return make_double2(x, y); }
+template <> __device__ __forceinline__ float2 mk2<float>(float x, float y) { return make_float2(x, y); }
+
+template <typename T> __device__ __forceinline__ T xfma(T a, T b, T c);
+template <> __device__ __forceinline__ double xfma<double>(double a, double b, double c) { return fma(a, b, c); }
+template <> __device__ __forceinline__ float xfma<float>(float a, float b, float c) { return fmaf(a, b, c); }
+
+template <typename T>
+struct Cplx {
+    T r, i;
+};
+
+template <typename T> __device__ __forceinline__ Cplx<T> cadd(Cplx<T> a, Cplx<T> b) { return {a.r + b.r, a.i + b.i}; }
+template <typename T> __device__ __forceinline__ Cplx<T> csub(Cplx<T> a, Cplx<T> b) { return {a.r - b.r, a.i - b.i}; }
+// -i * a
+template <typename T> __device__ __forceinline__ Cplx<T> cmuli_neg(Cplx<T> a) { return {a.i, -a.r}; }
+template <typename T> __device__ __forceinline__ Cplx<T> cmul(Cplx<T> a, Cplx<T> b)
 {
-    return BLDFM_ERR_INVALID;
+    return {xfma<T>(a.r, b.r, -(a.i * b.i)), xfma<T>(a.r, b.i, a.i * b.r)};
+}
+
+// ---- forward butterflies (w_r = exp(-2*pi*i/r)), in place on v[0..r-1]
+template <typename T> __device__ __forceinline__ void bfly2(Cplx<T>* v)
+{
+    const Cplx<T> a = v[0], b = v[1];
+    v[0] = cadd(a, b); v[1] = csub(a, b);
+}
+
+template <typename T> __device__ __forceinline__ void bfly3(Cplx<T>* v)
+{
+    const T s = (T)0.86602540378443864676;   // sin(2*pi/3)
+    const Cplx<T> t1 = cadd(v[1], v[2]);
+    const Cplx<T> m = {xfma<T>((T)-0.5, t1.r, v[0].r), xfma<T>((T)-0.5, t1.i, v[0].i)};
+    const Cplx<T> d = {s * (v[1].r - v[2].r), s * (v[1].i - v[2].i)};
+    v[0] = cadd(v[0], t1);
+    v[1] = {m.r + d.i, m.i - d.r};
+    v[2] = {m.r - d.i, m.i + d.r};
+}
+
+template <typename T> __device__ __forceinline__ void bfly4(Cplx<T>* v)
+{
+    const Cplx<T> a0 = cadd(v[0], v[2]), a1 = csub(v[0], v[2]);
+    const Cplx<T> a2 = cadd(v[1], v[3]), a3 = cmuli_neg(csub(v[1], v[3]));
+    v[0] = cadd(a0, a2); v[2] = csub(a0, a2);
+    v[1] = cadd(a1, a3); v[3] = csub(a1, a3);
+}
+
+template <typename T> __device__ __forceinline__ void bfly5(Cplx<T>* v)
+{
+    const T c1 = (T)0.30901699437494742410, c2 = (T)-0.80901699437494742410;
+    const T s1 = (T)0.95105651629515357212, s2 = (T)0.58778525229247312917;
+    const Cplx<T> t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
+    const Cplx<T> t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+    const Cplx<T> m1 = {xfma<T>(c1, t1.r, xfma<T>(c2, t2.r, v[0].r)), xfma<T>(c1, t1.i, xfma<T>(c2, t2.i, v[0].i))};
+    const Cplx<T> m2 = {xfma<T>(c2, t1.r, xfma<T>(c1, t2.r, v[0].r)), xfma<T>(c2, t1.i, xfma<T>(c1, t2.i, v[0].i))};
+    const Cplx<T> n1 = {xfma<T>(s1, t3.r, s2 * t4.r), xfma<T>(s1, t3.i, s2 * t4.i)};
+    const Cplx<T> n2 = {xfma<T>(s2, t3.r, -(s1 * t4.r)), xfma<T>(s2, t3.i, -(s1 * t4.i))};
+    v[0] = cadd(v[0], cadd(t1, t2));
+    v[1] = {m1.r + n1.i, m1.i - n1.r};     // m1 - i*n1
+    v[4] = {m1.r - n1.i, m1.i + n1.r};
+    v[2] = {m2.r + n2.i, m2.i - n2.r};
+    v[3] = {m2.r - n2.i, m2.i + n2.r};
+}
+
+template <typename T> __device__ __forceinline__ void bfly8(Cplx<T>* v)
+{
+    const T h = (T)0.70710678118654752440;
+    Cplx<T> e[4] = {v[0], v[2], v[4], v[6]};
+    Cplx<T> o[4] = {v[1], v[3], v[5], v[7]};
+    bfly4<T>(e);
+    bfly4<T>(o);
+    // o[k] *= w_8^k : w^1 = (1-i)/sqrt2, w^2 = -i, w^3 = (-1-i)/sqrt2
+    const Cplx<T> o1 = {h * (o[1].r + o[1].i), h * (o[1].i - o[1].r)};
+    const Cplx<T> o2 = cmuli_neg(o[2]);
+    const Cplx<T> o3 = {h * (o[3].i - o[3].r), -h * (o[3].r + o[3].i)};
+    v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
+    v[1] = cadd(e[1], o1);   v[5] = csub(e[1], o1);
+    v[2] = cadd(e[2], o2);   v[6] = csub(e[2], o2);
+    v[3] = cadd(e[3], o3);   v[7] = csub(e[3], o3);
+}
+
+template <typename T, int R>
+__device__ __forceinline__ void fft_stage(typename Vec2<T>::type* buf, const typename Vec2<T>::type* __restrict__ tw,
+                                          int N, int L, int cw)
+{
+    using V = typename Vec2<T>::type;
+    const int nbf = N / R;           // butterflies per transform
+    const int step = N / (L * R);    // twiddle stride
+    const int total = nbf * cw;
+    for (int b = threadIdx.x; b < total; b += kFftThreads) {
+        const int t = b / nbf;
+        const int jj = b - t * nbf;
+        const int blk = jj / L;
+        const int j = jj - blk * L;
+        V* p = buf + (size_t)t * (N + kFftPad) + (size_t)blk * L * R + j;
+        Cplx<T> v[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) { const V x = p[u * L]; v[u] = {x.x, x.y}; }
+        if (L > 1) {
+#pragma unroll
+            for (int u = 1; u < R; ++u) {
+                const V w = tw[(size_t)j * u * step];
+                v[u] = cmul<T>(v[u], Cplx<T>{w.x, w.y});
+            }
+        }
+        if (R == 2) bfly2<T>(v);
+        else if (R == 3) bfly3<T>(v);
+        else if (R == 4) bfly4<T>(v);
+        else if (R == 5) bfly5<T>(v);
+        else bfly8<T>(v);
+#pragma unroll
+        for (int u = 0; u < R; ++u) p[u * L] = mk2<T>(v[u].r, v[u].i);
+    }
+}
+
+// position of natural input index i in the digit-reversed DIT layout
+__device__ __forceinline__ int fft_digit_reverse(int i, const FftPassArgs& a)
+{
+    int pos = 0, ncur = a.N;
+    for (int s = a.nstages - 1; s >= 0; --s) {
+        const int r = a.radix[s];
+        const int q = i / r;
+        const int d = i - q * r;
+        ncur /= r;
+        pos += d * ncur;
+        i = q;
+    }
+    return pos;
+}
+
+// grid = (ceil(ntrans/cw), nfields) ; block = kFftThreads ; dynamic smem = cw*(N+pad)*sizeof(complex)
+template <typename T, bool REAL_OUT>
+__global__ void __launch_bounds__(kFftThreads)
+k_fft_pass(const FftPassArgs a)
+{
+    using V = typename Vec2<T>::type;
+    extern __shared__ __align__(16) unsigned char fft_smem[];
+    V* buf = reinterpret_cast<V*>(fft_smem);
+    const int N = a.N;
+    const int t0 = blockIdx.x * a.cw;
+    const int cw = min(a.cw, a.ntrans - t0);
+    const bool second = (int)blockIdx.y >= a.nfields_first;
+    const size_t field = second ? blockIdx.y - a.nfields_first : blockIdx.y;
+    const V* in = reinterpret_cast<const V*>(second ? a.in2 : a.in) + field * a.in_field_stride;
+    void* outp = second ? a.out2 : a.out;
+    const T sgn = a.conj_io ? (T)-1 : (T)1;
+
+    // zero fill, then scatter the nl non-zero inputs to their digit-reversed slots
+    for (int e = threadIdx.x; e < cw * (N + kFftPad); e += kFftThreads) buf[e] = mk2<T>((T)0, (T)0);
+    __syncthreads();
+    const int npos = (a.nl + 1) / 2;
+    for (int e = threadIdx.x; e < cw * a.nl; e += kFftThreads) {
+        int t, k;
+        if (a.t_fast) { k = e / cw; t = e - k * cw; }
+        else          { t = e / a.nl; k = e - t * a.nl; }
+        const int i = k < npos ? k : k - a.nl + N;
+        const V x = in[(size_t)(t0 + t) * a.in_tstride + (size_t)k * a.in_kstride];
+        buf[(size_t)t * (N + kFftPad) + fft_digit_reverse(i, a)] = mk2<T>(x.x, sgn * x.y);
+    }
+    __syncthreads();
+
+    const V* tw = reinterpret_cast<const V*>(a.twiddle);
+    int L = 1;
+    for (int s = 0; s < a.nstages; ++s) {
+        const int r = a.radix[s];
+        switch (r) {
+            case 2: fft_stage<T, 2>(buf, tw, N, L, cw); break;
+            case 3: fft_stage<T, 3>(buf, tw, N, L, cw); break;
+            case 4: fft_stage<T, 4>(buf, tw, N, L, cw); break;
+            case 5: fft_stage<T, 5>(buf, tw, N, L, cw); break;
+            default: fft_stage<T, 8>(buf, tw, N, L, cw); break;
+        }
+        L *= r;
+        __syncthreads();
+    }
+
+    // store the output window
+    for (int e = threadIdx.x; e < cw * a.nwin; e += kFftThreads) {
+        int t, j;
+        if (a.t_fast) { j = e / cw; t = e - j * cw; }
+        else          { t = e / a.nwin; j = e - t * a.nwin; }
+        const V x = buf[(size_t)t * (N + kFftPad) + a.win0 + j];
+        const size_t o = field * a.out_field_stride + (size_t)(t0 + t) * a.out_tstride +
+                         (size_t)j * a.out_jstride;
+        if (REAL_OUT) reinterpret_cast<T*>(outp)[o] = x.x;
+        else reinterpret_cast<V*>(outp)[o] = mk2<T>(x.x, sgn * x.y);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+inline bool fft_factorize(int n, std::vector<int>& radix)
+{
+    radix.clear();
+    if (n < 1) return false;
+    std::vector<int> small;   // 3s and 5s first (keeps the power-of-two stages' strides aligned)
+    while (n % 3 == 0) { small.push_back(3); n /= 3; }
+    while (n % 5 == 0) { small.push_back(5); n /= 5; }
+    std::vector<int> pow2;
+    while (n % 8 == 0) { pow2.push_back(8); n /= 8; }
+    while (n % 4 == 0) { pow2.push_back(4); n /= 4; }
+    while (n % 2 == 0) { pow2.push_back(2); n /= 2; }
+    if (n != 1) return false;
+    radix = small;
+    radix.insert(radix.end(), pow2.begin(), pow2.end());
+    if (radix.empty()) radix.push_back(1);
+    return (int)radix.size() <= kFftMaxStages;
+}
+
+inline size_t fft_smem_bytes(int N, int cw, bool f32)
+{
+    return (size_t)cw * (size_t)(N + kFftPad) * (f32 ? sizeof(float2) : sizeof(double2));
+}
+
+// transforms per CTA for the two passes given the shared-memory budget
+inline int fft_pick_cw(int N, bool f32, size_t smem_optin, int want)
+{
+    int cw = want;
+    while (cw > 1 && fft_smem_bytes(N, cw, f32) > smem_optin / 2) cw /= 2;   // keep >= 2 CTAs / SM
+    return cw;
+}
+
+inline bool pruned_fft_supported(const bldfm_geometry& g, bool f32, size_t smem_optin)
+{
+    std::vector<int> r;
+    if (g.nfx < 2 || g.nfy < 2) return false;
+    if (!fft_factorize(g.nfx, r) || !fft_factorize(g.nfy, r)) return false;
+    if (g.px + g.nx > g.nfx || g.py + g.ny > g.nfy) return false;
+    return fft_smem_bytes(g.nfx, 1, f32) <= smem_optin && fft_smem_bytes(g.nfy, 1, f32) <= smem_optin;
+}
+
+inline size_t pruned_fft_work_bytes(const bldfm_geometry& g, bool f32, int64_t nfields)
+{
+    const int64_t chunk = std::min<int64_t>(nfields, 16384);
+    return (size_t)2 * (size_t)chunk * (size_t)g.nly * (size_t)g.nx * (f32 ? sizeof(float2) : sizeof(double2));
+}
+
+// exp(-2*pi*i*k/N) evaluated in x87 extended precision and rounded to double (host)
+inline void fft_twiddles(int N, std::vector<double>& out)
+{
+    out.resize((size_t)2 * N);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int k = 0; k < N; ++k) {
+        const long double x = two_pi * (long double)k / (long double)N;
+        out[(size_t)2 * k] = (double)cosl(x);
+        out[(size_t)2 * k + 1] = (double)(-sinl(x));
+    }
+}
+
+struct PrunedFftTables {
+    const void* tw_x = nullptr;   // device, compute type
+    const void* tw_y = nullptr;
+};
+
+// Runs both passes for the `nfields` compact spectra of spec_p (-> out_p) and of spec_q (-> out_q)
+// in two launches.  `work` holds 2*nfields intermediate fields [nly][nx] complex.
+template <typename T>
+inline cudaError_t pruned_fft_launch(cudaStream_t stream, size_t smem_optin, const bldfm_geometry& g,
+                                     bool forward_dir, const void* spec_p, const void* spec_q,
+                                     int64_t nfields, void* work, void* out_p, void* out_q,
+                                     const PrunedFftTables& tab, int* nlaunch)
+{
+    using V = typename Vec2<T>::type;
+    const bool f32 = sizeof(T) == 4;
+    std::vector<int> rx, ry;
+    fft_factorize(g.nfx, rx);
+    fft_factorize(g.nfy, ry);
+
+    FftPassArgs ax{};
+    ax.N = g.nfx; ax.nstages = (int)rx.size();
+    for (size_t i = 0; i < rx.size(); ++i) ax.radix[i] = rx[i];
+    ax.nl = g.nlx; ax.win0 = g.px; ax.nwin = g.nx;
+    ax.cw = fft_pick_cw(g.nfx, f32, smem_optin, 4);
+    ax.ntrans = g.nly; ax.t_fast = 0; ax.conj_io = forward_dir ? 0 : 1;
+    ax.in_field_stride = (int64_t)g.nly * g.nlx; ax.in_tstride = g.nlx; ax.in_kstride = 1;
+    ax.out_field_stride = (int64_t)g.nly * g.nx; ax.out_tstride = g.nx; ax.out_jstride = 1;
+    ax.twiddle = tab.tw_x;
+
+    FftPassArgs ay{};
+    ay.N = g.nfy; ay.nstages = (int)ry.size();
+    for (size_t i = 0; i < ry.size(); ++i) ay.radix[i] = ry[i];
+    ay.nl = g.nly; ay.win0 = g.py; ay.nwin = g.ny;
+    ay.cw = fft_pick_cw(g.nfy, f32, smem_optin, 4);
+    ay.ntrans = g.nx; ay.t_fast = 1; ay.conj_io = forward_dir ? 0 : 1;
+    ay.in_field_stride = (int64_t)g.nly * g.nx; ay.in_tstride = 1; ay.in_kstride = g.nx;
+    ay.out_field_stride = (int64_t)g.ny * g.nx; ay.out_tstride = 1; ay.out_jstride = g.nx;
+    ay.twiddle = tab.tw_y;
+
+    const size_t sx = fft_smem_bytes(ax.N, ax.cw, f32), sy = fft_smem_bytes(ay.N, ay.cw, f32);
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_fft_pass<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fft_pass<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    if (e != cudaSuccess) return e;
+
+    // gridDim.y is limited to 65535: split the field batch if needed
+    const int64_t chunk = 16384;
+    for (int64_t f0 = 0; f0 < nfields; f0 += chunk) {
+        const int nf = (int)std::min<int64_t>(chunk, nfields - f0);
+        FftPassArgs bx = ax, by = ay;
+        bx.nfields_first = nf; by.nfields_first = nf;
+        bx.in = reinterpret_cast<const V*>(spec_p) + (size_t)f0 * ax.in_field_stride;
+        bx.in2 = reinterpret_cast<const V*>(spec_q) + (size_t)f0 * ax.in_field_stride;
+        bx.out = reinterpret_cast<V*>(work);
+        bx.out2 = reinterpret_cast<V*>(work) + (size_t)nf * ax.out_field_stride;
+        by.in = bx.out; by.in2 = bx.out2;
+        by.out = reinterpret_cast<T*>(out_p) + (size_t)f0 * ay.out_field_stride;
+        by.out2 = reinterpret_cast<T*>(out_q) + (size_t)f0 * ay.out_field_stride;
+        k_fft_pass<T, false><<<dim3((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), (unsigned)(2 * nf)), kFftThreads, sx, stream>>>(bx);
+        k_fft_pass<T, true><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), (unsigned)(2 * nf)), kFftThreads, sy, stream>>>(by);
+        *nlaunch += 2;
+    }
+    return cudaGetLastError();
 }
 
 }  // namespace bldfm

@@ -14,6 +14,7 @@ import numpy as np
 
 from . import _lib
 from . import config
+from ._pinned import pool as _pinned_pool
 from .fft_manager import get_fft_manager
 
 logger = logging.getLogger("bldfm.solver")
@@ -37,6 +38,20 @@ def _flags(footprint, analytic, precision):
     if config.FFT_LIBRARY:
         f |= _lib.FFT_LIBRARY
     return f
+
+
+_GEOM_CACHE = {}
+
+
+def _geometry(shape, domain, modes, halo):
+    key = (tuple(shape), float(domain[0]), float(domain[1]), int(modes[0]), int(modes[1]),
+           None if halo is None else float(halo))
+    g = _GEOM_CACHE.get(key)
+    if g is None:
+        g = _lib.geometry(shape, domain, modes, halo)
+        if len(_GEOM_CACHE) < 256:
+            _GEOM_CACHE[key] = g
+    return g
 
 
 def _levels_array(levels):
@@ -89,7 +104,7 @@ def steady_state_transport_solver(
     if q0.ndim != 2:
         raise ValueError("srf_flx must be a 2D array")
     ny, nx = q0.shape
-    geom = _lib.geometry(q0.shape, domain, modes, halo)                    # raises for odd modes (:90-91)
+    geom = _geometry(q0.shape, domain, modes, halo)                        # raises for odd modes (:90-91)
     if geom.clamped:                                                       # solver.py:122-127
         logger.info("Warning: Number of Fourier modes must not exeed number of grid cells.")
         logger.info("Setting both equal.")
@@ -100,8 +115,8 @@ def steady_state_transport_solver(
     prob, keep = _lib.make_problem(z, profiles, meas_pt, srf_bg_conc)
     f32 = bool(_lib.lib().bldfm_output_is_f32(flags, prob.xm, prob.ym))
     dt = np.float32 if f32 else np.float64
-    conc = np.empty((nlv, ny, nx), dtype=dt)
-    flx = np.empty((nlv, ny, nx), dtype=dt)
+    conc = _pinned_pool.empty((nlv, ny, nx), dt)
+    flx = _pinned_pool.empty((nlv, ny, nx), dt)
     src = None
     if not footprint:
         src = _lib.as_f64(q0)
