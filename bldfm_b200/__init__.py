@@ -6,13 +6,30 @@ C ABI of include/bldfm_b200.h.  No CPU fallback: without the built library and a
 compute calls raise.
 """
 
-from .solver import steady_state_transport_solver, ivp_solver  # noqa: F401
+from .solver import steady_state_transport_solver, ivp_solver, solve_batched  # noqa: F401
+from .utils import compute_wind_fields, ideal_source, point_measurement  # noqa: F401
+from .interface import (  # noqa: F401
+    run_bldfm_single,
+    run_bldfm_timeseries,
+    run_bldfm_multitower,
+    run_bldfm_parallel,
+)
+from .cache import GreensFunctionCache  # noqa: F401
 from .fft_manager import get_fft_manager, reset_fft_manager  # noqa: F401
 from . import config  # noqa: F401
 
 __all__ = [
     "steady_state_transport_solver",
     "ivp_solver",
+    "solve_batched",
+    "compute_wind_fields",
+    "ideal_source",
+    "point_measurement",
+    "run_bldfm_single",
+    "run_bldfm_timeseries",
+    "run_bldfm_multitower",
+    "run_bldfm_parallel",
+    "GreensFunctionCache",
     "get_fft_manager",
     "reset_fft_manager",
     "config",

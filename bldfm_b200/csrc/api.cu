@@ -438,6 +438,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
 
     // ---- K1-K3: spectrum of the padded source (non-footprint)
     const double2* d_src_spec = nullptr;
+    bool src_compact = false;
     if (!footprint) {
         const double* d_q0 = srf_flx;
         if (!(flags & BLDFM_SRC_ON_DEVICE)) {
@@ -446,16 +447,34 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
                                      cudaMemcpyHostToDevice, pl->stream));
             d_q0 = static_cast<const double*>(pl->src_in.p);
         }
-        TRY(pl->src_pad.ensure(sizeof(double2) * (size_t)g.nxe * g.nye));
-        double2* d_pad = static_cast<double2*>(pl->src_pad.p);
-        k_pad_source<<<grid_for((int64_t)g.nxe * g.nye, 256, pl->num_sms), 256, 0, pl->stream>>>(
-            d_q0, d_pad, g.nx, g.ny, g.px, g.py, g.nxe, g.nye);
-        pl->launches++;
-        cufftHandle h;
-        TRY(get_fft_plan(pl, g.nye, g.nxe, CUFFT_Z2Z, 1, &h));
-        CUFFT_TRY(cufftExecZ2Z(h, reinterpret_cast<cufftDoubleComplex*>(d_pad),
-                               reinterpret_cast<cufftDoubleComplex*>(d_pad), CUFFT_FORWARD));
-        d_src_spec = d_pad;
+        const bool lib_fwd = (flags & BLDFM_FFT_LIBRARY) || !pruned_fft_supported(g, false, pl->smem_optin) ||
+                             g.nfx != g.nxe || g.nfy != g.nye;
+        if (lib_fwd) {
+            TRY(pl->src_pad.ensure(sizeof(double2) * (size_t)g.nxe * g.nye));
+            double2* d_pad = static_cast<double2*>(pl->src_pad.p);
+            k_pad_source<<<grid_for((int64_t)g.nxe * g.nye, 256, pl->num_sms), 256, 0, pl->stream>>>(
+                d_q0, d_pad, g.nx, g.ny, g.px, g.py, g.nxe, g.nye);
+            pl->launches++;
+            cufftHandle h;
+            TRY(get_fft_plan(pl, g.nye, g.nxe, CUFFT_Z2Z, 1, &h));
+            CUFFT_TRY(cufftExecZ2Z(h, reinterpret_cast<cufftDoubleComplex*>(d_pad),
+                                   reinterpret_cast<cufftDoubleComplex*>(d_pad), CUFFT_FORWARD));
+            d_src_spec = d_pad;
+        } else {
+            // pruned: [ny][nlx] intermediate + compact [nly][nlx] spectrum
+            const size_t wbytes = sizeof(double2) * (size_t)g.ny * g.nlx;
+            const size_t sbytes = sizeof(double2) * (size_t)g.nly * g.nlx;
+            TRY(pl->src_pad.ensure(wbytes + sbytes));
+            char* base = static_cast<char*>(pl->src_pad.p);
+            PrunedFftTables tab;
+            TRY(ensure_twiddles(pl, false, &tab));
+            int nl = 0;
+            cudaError_t fe = pruned_fft_forward(pl->stream, pl->smem_optin, g, d_q0, base, base + wbytes, tab, &nl);
+            if (fe != cudaSuccess) return fail(BLDFM_ERR_CUDA, std::string("pruned forward FFT: ") + cudaGetErrorString(fe));
+            pl->launches += nl;
+            d_src_spec = reinterpret_cast<const double2*>(base + wbytes);
+            src_compact = true;
+        }
     }
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev[1], pl->stream));
 
@@ -473,7 +492,9 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         a.single = dbl ? 0 : 1;
         a.out_f32 = spec_f32 ? 1 : 0;
         a.footprint = footprint ? 1 : 0;
-        a.src_pitch = g.nxe; a.src_nfx = g.nxe; a.src_nfy = g.nye;
+        a.src_pitch = src_compact ? g.nlx : g.nxe;
+        a.src_nfx = src_compact ? g.nlx : g.nxe;
+        a.src_nfy = src_compact ? g.nly : g.nye;
         a.q0_const = 1.0 / g.nxe / g.nye;                           // solver.py:134
         a.src_scale = 1.0 / ((double)g.nxe * (double)g.nye);        // norm="forward"
         a.src_spec = d_src_spec;

@@ -32,8 +32,11 @@ struct FftPassArgs {
     int32_t N;                 // transform length
     int32_t nstages;
     int32_t radix[kFftMaxStages];
-    int32_t nl;                // non-zero inputs (fftfreq order: 0..(nl-1)/2, -(nl/2)..-1)
-    int32_t win0, nwin;        // output window [win0, win0+nwin)
+    // inputs : in_freq ? n_in entries in fftfreq order (0..(n-1)/2, -(n/2)..-1)
+    //                    : a window [in_off, in_off + n_in) ; everything else is zero
+    // outputs: out_freq ? n_out entries in fftfreq order : the window [out_off, out_off + n_out)
+    int32_t in_freq, n_in, in_off;
+    int32_t out_freq, n_out, out_off;
     int32_t cw;                // transforms per CTA
     int32_t ntrans;            // transforms per field
     int32_t t_fast;            // 1: consecutive threads walk the transform index first
@@ -184,7 +187,7 @@ __device__ __forceinline__ int fft_digit_reverse(int i, const FftPassArgs& a)
 }
 
 // grid = (ceil(ntrans/cw), nfields) ; block = kFftThreads ; dynamic smem = cw*(N+pad)*sizeof(complex)
-template <typename T, bool REAL_OUT>
+template <typename T, bool REAL_IN, bool REAL_OUT>
 __global__ void __launch_bounds__(kFftThreads)
 k_fft_pass(const FftPassArgs a)
 {
@@ -196,21 +199,24 @@ k_fft_pass(const FftPassArgs a)
     const int cw = min(a.cw, a.ntrans - t0);
     const bool second = (int)blockIdx.y >= a.nfields_first;
     const size_t field = second ? blockIdx.y - a.nfields_first : blockIdx.y;
-    const V* in = reinterpret_cast<const V*>(second ? a.in2 : a.in) + field * a.in_field_stride;
+    const void* inp = second ? a.in2 : a.in;
     void* outp = second ? a.out2 : a.out;
     const T sgn = a.conj_io ? (T)-1 : (T)1;
 
-    // zero fill, then scatter the nl non-zero inputs to their digit-reversed slots
+    // zero fill, then scatter the non-zero inputs to their digit-reversed slots
     for (int e = threadIdx.x; e < cw * (N + kFftPad); e += kFftThreads) buf[e] = mk2<T>((T)0, (T)0);
     __syncthreads();
-    const int npos = (a.nl + 1) / 2;
-    for (int e = threadIdx.x; e < cw * a.nl; e += kFftThreads) {
+    const int npos_in = (a.n_in + 1) / 2;
+    for (int e = threadIdx.x; e < cw * a.n_in; e += kFftThreads) {
         int t, k;
         if (a.t_fast) { k = e / cw; t = e - k * cw; }
-        else          { t = e / a.nl; k = e - t * a.nl; }
-        const int i = k < npos ? k : k - a.nl + N;
-        const V x = in[(size_t)(t0 + t) * a.in_tstride + (size_t)k * a.in_kstride];
-        buf[(size_t)t * (N + kFftPad) + fft_digit_reverse(i, a)] = mk2<T>(x.x, sgn * x.y);
+        else          { t = e / a.n_in; k = e - t * a.n_in; }
+        const int i = a.in_freq ? (k < npos_in ? k : k - a.n_in + N) : a.in_off + k;
+        const size_t g = field * a.in_field_stride + (size_t)(t0 + t) * a.in_tstride + (size_t)k * a.in_kstride;
+        T xr, xi;
+        if (REAL_IN) { xr = reinterpret_cast<const T*>(inp)[g]; xi = (T)0; }
+        else { const V x = reinterpret_cast<const V*>(inp)[g]; xr = x.x; xi = x.y; }
+        buf[(size_t)t * (N + kFftPad) + fft_digit_reverse(i, a)] = mk2<T>(xr, sgn * xi);
     }
     __syncthreads();
 
@@ -229,12 +235,14 @@ k_fft_pass(const FftPassArgs a)
         __syncthreads();
     }
 
-    // store the output window
-    for (int e = threadIdx.x; e < cw * a.nwin; e += kFftThreads) {
+    // store the requested outputs
+    const int npos_out = (a.n_out + 1) / 2;
+    for (int e = threadIdx.x; e < cw * a.n_out; e += kFftThreads) {
         int t, j;
         if (a.t_fast) { j = e / cw; t = e - j * cw; }
-        else          { t = e / a.nwin; j = e - t * a.nwin; }
-        const V x = buf[(size_t)t * (N + kFftPad) + a.win0 + j];
+        else          { t = e / a.n_out; j = e - t * a.n_out; }
+        const int i = a.out_freq ? (j < npos_out ? j : j - a.n_out + N) : a.out_off + j;
+        const V x = buf[(size_t)t * (N + kFftPad) + i];
         const size_t o = field * a.out_field_stride + (size_t)(t0 + t) * a.out_tstride +
                          (size_t)j * a.out_jstride;
         if (REAL_OUT) reinterpret_cast<T*>(outp)[o] = x.x;
@@ -325,7 +333,7 @@ inline cudaError_t pruned_fft_launch(cudaStream_t stream, size_t smem_optin, con
     FftPassArgs ax{};
     ax.N = g.nfx; ax.nstages = (int)rx.size();
     for (size_t i = 0; i < rx.size(); ++i) ax.radix[i] = rx[i];
-    ax.nl = g.nlx; ax.win0 = g.px; ax.nwin = g.nx;
+    ax.in_freq = 1; ax.n_in = g.nlx; ax.in_off = 0; ax.out_freq = 0; ax.n_out = g.nx; ax.out_off = g.px;
     ax.cw = fft_pick_cw(g.nfx, f32, smem_optin, 4);
     ax.ntrans = g.nly; ax.t_fast = 0; ax.conj_io = forward_dir ? 0 : 1;
     ax.in_field_stride = (int64_t)g.nly * g.nlx; ax.in_tstride = g.nlx; ax.in_kstride = 1;
@@ -335,7 +343,7 @@ inline cudaError_t pruned_fft_launch(cudaStream_t stream, size_t smem_optin, con
     FftPassArgs ay{};
     ay.N = g.nfy; ay.nstages = (int)ry.size();
     for (size_t i = 0; i < ry.size(); ++i) ay.radix[i] = ry[i];
-    ay.nl = g.nly; ay.win0 = g.py; ay.nwin = g.ny;
+    ay.in_freq = 1; ay.n_in = g.nly; ay.in_off = 0; ay.out_freq = 0; ay.n_out = g.ny; ay.out_off = g.py;
     ay.cw = fft_pick_cw(g.nfy, f32, smem_optin, 4);
     ay.ntrans = g.nx; ay.t_fast = 1; ay.conj_io = forward_dir ? 0 : 1;
     ay.in_field_stride = (int64_t)g.nly * g.nx; ay.in_tstride = 1; ay.in_kstride = g.nx;
@@ -344,9 +352,9 @@ inline cudaError_t pruned_fft_launch(cudaStream_t stream, size_t smem_optin, con
 
     const size_t sx = fft_smem_bytes(ax.N, ax.cw, f32), sy = fft_smem_bytes(ay.N, ay.cw, f32);
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_fft_pass<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    e = cudaFuncSetAttribute(k_fft_pass<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_fft_pass<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    e = cudaFuncSetAttribute(k_fft_pass<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
     if (e != cudaSuccess) return e;
 
     // gridDim.y is limited to 65535: split the field batch if needed
@@ -362,10 +370,53 @@ inline cudaError_t pruned_fft_launch(cudaStream_t stream, size_t smem_optin, con
         by.in = bx.out; by.in2 = bx.out2;
         by.out = reinterpret_cast<T*>(out_p) + (size_t)f0 * ay.out_field_stride;
         by.out2 = reinterpret_cast<T*>(out_q) + (size_t)f0 * ay.out_field_stride;
-        k_fft_pass<T, false><<<dim3((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), (unsigned)(2 * nf)), kFftThreads, sx, stream>>>(bx);
-        k_fft_pass<T, true><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), (unsigned)(2 * nf)), kFftThreads, sy, stream>>>(by);
+        k_fft_pass<T, false, false><<<dim3((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), (unsigned)(2 * nf)), kFftThreads, sx, stream>>>(bx);
+        k_fft_pass<T, false, true><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), (unsigned)(2 * nf)), kFftThreads, sy, stream>>>(by);
         *nlaunch += 2;
     }
+    return cudaGetLastError();
+}
+
+// Pruned forward transform of the padded source (K1+K2+K3 fused): q0[ny][nx] real (its zero halo is
+// implicit) -> unnormalised spectrum on the retained modes, compact [nly][nlx] c128.
+// `work` holds [ny][nlx] c128.  Two launches.
+inline cudaError_t pruned_fft_forward(cudaStream_t stream, size_t smem_optin, const bldfm_geometry& g,
+                                      const double* q0, void* work, void* spec, const PrunedFftTables& tab,
+                                      int* nlaunch)
+{
+    std::vector<int> rx, ry;
+    fft_factorize(g.nxe, rx);
+    fft_factorize(g.nye, ry);
+    FftPassArgs ax{};
+    ax.N = g.nxe; ax.nstages = (int)rx.size();
+    for (size_t i = 0; i < rx.size(); ++i) ax.radix[i] = rx[i];
+    ax.in_freq = 0; ax.n_in = g.nx; ax.in_off = g.px; ax.out_freq = 1; ax.n_out = g.nlx; ax.out_off = 0;
+    ax.cw = fft_pick_cw(g.nxe, false, smem_optin, 4);
+    ax.ntrans = g.ny; ax.t_fast = 0; ax.conj_io = 0;
+    ax.in_field_stride = 0; ax.in_tstride = g.nx; ax.in_kstride = 1;
+    ax.out_field_stride = 0; ax.out_tstride = g.nlx; ax.out_jstride = 1;
+    ax.nfields_first = 1; ax.in = q0; ax.in2 = q0; ax.out = work; ax.out2 = work; ax.twiddle = tab.tw_x;
+
+    FftPassArgs ay{};
+    ay.N = g.nye; ay.nstages = (int)ry.size();
+    for (size_t i = 0; i < ry.size(); ++i) ay.radix[i] = ry[i];
+    ay.in_freq = 0; ay.n_in = g.ny; ay.in_off = g.py; ay.out_freq = 1; ay.n_out = g.nly; ay.out_off = 0;
+    ay.cw = fft_pick_cw(g.nye, false, smem_optin, 4);
+    ay.ntrans = g.nlx; ay.t_fast = 1; ay.conj_io = 0;
+    ay.in_field_stride = 0; ay.in_tstride = 1; ay.in_kstride = g.nlx;
+    ay.out_field_stride = 0; ay.out_tstride = 1; ay.out_jstride = g.nlx;
+    ay.nfields_first = 1; ay.in = work; ay.in2 = work; ay.out = spec; ay.out2 = spec; ay.twiddle = tab.tw_y;
+
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_fft_pass<double, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fft_pass<double, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    if (e != cudaSuccess) return e;
+    k_fft_pass<double, true, false><<<dim3((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), 1), kFftThreads,
+                                      fft_smem_bytes(ax.N, ax.cw, false), stream>>>(ax);
+    k_fft_pass<double, false, false><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), 1), kFftThreads,
+                                       fft_smem_bytes(ay.N, ay.cw, false), stream>>>(ay);
+    *nlaunch += 2;
     return cudaGetLastError();
 }
 

@@ -136,6 +136,49 @@ def steady_state_transport_solver(
     return result
 
 
+def solve_batched(srf_flx, zs, profiles_list, domain, levels, modes=(512, 512), meas_pts=None,
+                  srf_bg_conc=0.0, footprint=False, analytic=False, halo=None, precision="single"):
+    """Many (tower, met) conditions in ONE launch (C entry point ``bldfm_solve_batched``).
+
+    ``zs[b]``, ``profiles_list[b]``, ``meas_pts[b]`` describe problem b; everything else is shared.
+    Problems with byte-identical (z, profiles) share one vertical march.  Returns
+    ``(conc, flx)`` of shape ``[B, nlv, ny, nx]`` (float32 only for precision="single" without any
+    phase shift, like the single-problem solver).
+    """
+    q0 = np.asarray(srf_flx)
+    ny, nx = q0.shape
+    B = len(zs)
+    if B < 1:
+        raise ValueError("solve_batched needs at least one problem")
+    if meas_pts is None:
+        meas_pts = [(0.0, 0.0)] * B
+    geom = _geometry(q0.shape, domain, modes, halo)
+    if geom.clamped:
+        logger.info("Warning: Number of Fourier modes must not exeed number of grid cells.")
+        logger.info("Setting both equal.")
+    flags = _flags(footprint, analytic, precision)
+    _, lv64 = _levels_array(levels)
+    nlv = len(lv64)
+    bg = srf_bg_conc if np.ndim(srf_bg_conc) else [srf_bg_conc] * B
+    probs, keep = [], []
+    for b in range(B):
+        p, k = _lib.make_problem(zs[b], profiles_list[b], meas_pts[b], bg[b])
+        probs.append(p)
+        keep.append(k)
+    f32 = all(bool(_lib.lib().bldfm_output_is_f32(flags, p.xm, p.ym)) for p in probs)
+    dt = np.float32 if f32 else np.float64
+    conc = _pinned_pool.empty((B, nlv, ny, nx), dt)
+    flx = _pinned_pool.empty((B, nlv, ny, nx), dt)
+    src = None if footprint else _lib.as_f64(q0)
+    parr = (_lib.Problem * B)(*probs)
+    plan = get_fft_manager().plan(geom)
+    _lib.check(_lib.lib().bldfm_solve_batched(
+        plan, B, parr, lv64.ctypes.data_as(C.POINTER(C.c_int64)), nlv,
+        None if src is None else _lib.ptr(src), flags, _lib.ptr(conc), _lib.ptr(flx)))
+    del keep
+    return conc, flx
+
+
 def spectral_fields(srf_flx, z, profiles, domain, levels, modes=(512, 512), meas_pt=(0.0, 0.0),
                     srf_bg_conc=0.0, footprint=False, analytic=False, halo=None,
                     precision="single"):

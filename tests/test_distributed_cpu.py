@@ -1,0 +1,110 @@
+"""CPU tests (gloo, world_size 2) of the multi-GPU host logic: sharding by march group, the final
+gather and the run_bldfm_parallel protocol with a stand-in for the CUDA solve."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_shard_groups_balanced_and_deterministic():
+    from bldfm_b200.distributed import owner_of_tasks, shard_groups
+    keys = [(10.0, i) for i in range(37)]
+    costs = [1.0 + 0.15 * (1 + i % 4) for i in range(37)]
+    a = shard_groups(keys, costs, 4)
+    b = shard_groups(keys, costs, 4)
+    assert a == b
+    assert sorted(g for r in a for g in r) == list(range(37))
+    loads = [sum(costs[g] for g in r) for r in a]
+    assert max(loads) - min(loads) <= max(costs)
+    owner = owner_of_tasks([0, 0, 1, 2, 36], a)
+    assert owner[0] == owner[1]
+
+
+def _fake_config():
+    from bldfm_b200.schema import Config, Domain, Met, Parallel, SolverOptions, Tower
+    towers = [Tower("A", 10.0, 100.0, 200.0), Tower("B", 10.0, 300.0, 250.0), Tower("C", 5.0, 50.0, 60.0)]
+    met = Met(ustar=[0.4, 0.5, 0.3, 0.45, 0.35], mol=[-50.0, -80.0, 100.0, 1e9, -200.0],
+              wind_speed=[4.0, 5.0, 3.0, 6.0, 2.0], wind_dir=[270.0, 250.0, 200.0, 10.0, 90.0])
+    return Config(Domain(nx=16, ny=12, xmax=400.0, ymax=300.0, nz=8, modes=(16, 12)), towers, met,
+                  SolverOptions(footprint=True, precision="double"), Parallel())
+
+
+def _fake_solve_tasks(config, tasks, surface_flux=None, cache=None):
+    """Stand-in for the CUDA path: fields are a deterministic function of (tower, met index)."""
+    from bldfm_b200 import interface
+    out = []
+    for ti, mi in tasks:
+        tower = config.towers[ti]
+        step = config.met.get_step(mi)
+        base = np.arange(12 * 16, dtype=np.float64).reshape(12, 16)
+        out.append(interface._result(tower, step, (None, None, None), base * (ti + 1) + mi, base - 7 * ti + mi * mi))
+    return out
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, str(ROOT))
+    import torch.distributed as dist
+    from bldfm_b200 import interface
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        interface.solve_tasks = _fake_solve_tasks
+        interface.solve_shape = lambda cfg: ((12, 16), np.float64)
+        interface.make_grid = lambda *a, **k: (None, None, None)
+        interface._profiles_for = lambda cfg, zm, step: (np.zeros(3), None)
+        cfg = _fake_config()
+        res = interface.run_bldfm_parallel(cfg, parallel_over="both")
+        part = interface.run_bldfm_parallel(cfg, parallel_over="time", gather=False)
+        nloc = sum(r is not None for lst in part.values() for r in lst)
+        if rank == 0:
+            q.put(("full", {k: [(r["conc"], r["flx"], r["timestamp"]) for r in v] for k, v in res.items()}))
+        else:
+            assert res == {}
+        q.put(("count", rank, nloc))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_run_bldfm_parallel_two_ranks_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    msgs = [q.get(timeout=120) for _ in range(3)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    full = next(m[1] for m in msgs if m[0] == "full")
+    counts = {m[1]: m[2] for m in msgs if m[0] == "count"}
+    cfg = _fake_config()
+    assert sum(counts.values()) == 15 and min(counts.values()) >= 5
+    expect = _fake_solve_tasks(cfg, [(ti, mi) for ti in range(3) for mi in range(5)])
+    k = 0
+    for ti, tower in enumerate(cfg.towers):
+        for mi in range(5):
+            conc, flx, ts = full[tower.name][mi]
+            assert np.array_equal(conc, expect[k]["conc"]) and np.array_equal(flx, expect[k]["flx"])
+            assert ts == mi
+            k += 1
+
+
+def test_plan_tasks_groups_towers_by_height():
+    from bldfm_b200.interface import plan_tasks
+    cfg = _fake_config()
+    tasks = [(ti, mi) for mi in range(5) for ti in range(3)]
+    keys, tg = plan_tasks(cfg, tasks)
+    assert len(keys) == 10                      # 2 distinct heights x 5 met steps
+    assert tg[0] == tg[1] != tg[2]              # towers A and B (z_m = 10) share a march

@@ -1,0 +1,86 @@
+"""GPU tests of the batched drivers (interface.py mirror) against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _config(footprint=True, precision="double", full_output=False):
+    from bldfm_b200.schema import Config, Domain, Met, Parallel, SolverOptions, Tower
+    towers = [Tower("A", 10.0, 400.0, 400.0), Tower("B", 10.0, 560.0, 320.0), Tower("C", 6.0, 240.0, 480.0)]
+    met = Met(ustar=[0.4, 0.5, 0.3, 0.45], mol=[-50.0, -80.0, 100.0, 1e9],
+              wind_speed=[4.0, 5.0, 3.0, 6.0], wind_dir=[270.0, 250.0, 200.0, 10.0])
+    dom = Domain(nx=64, ny=48, xmax=960.0, ymax=720.0, nz=16, modes=(64, 48), full_output=full_output)
+    return Config(dom, towers, met, SolverOptions(footprint=footprint, precision=precision), Parallel())
+
+
+def _oracle_result(oracle, cfg, tower, mi):
+    from bldfm_b200 import interface
+    step = cfg.met.get_step(mi)
+    z, prof = interface._profiles_for(cfg, tower.z_m, step)
+    dom, sol = cfg.domain, cfg.solver
+    return oracle.solve(interface._surface_flux(cfg, None), z, prof, (dom.xmax, dom.ymax), interface._levels(cfg),
+                        modes=dom.modes, meas_pt=(tower.x, tower.y), footprint=sol.footprint, halo=dom.halo,
+                        precision=sol.precision)
+
+
+@pytest.mark.parametrize("footprint", [True, False])
+def test_multitower_matches_oracle_and_single(gpu_lib, oracle, footprint):
+    import bldfm_b200
+    cfg = _config(footprint=footprint)
+    res = bldfm_b200.run_bldfm_multitower(cfg)
+    assert set(res) == {"A", "B", "C"}
+    for tower in cfg.towers:
+        assert len(res[tower.name]) == 4
+        for mi, r in enumerate(res[tower.name]):
+            grid, oc, of = _oracle_result(oracle, cfg, tower, mi)
+            assert r["conc"].shape == oc.shape
+            assert rel_l2(r["conc"], oc) <= 1e-10 and rel_l2(r["flx"], of) <= 1e-10
+            assert r["tower_name"] == tower.name and r["timestamp"] == mi
+            assert r["tower_xy"] == (tower.x, tower.y)
+            for a, b in zip(r["grid"], grid):
+                assert np.array_equal(a, b)
+            single = bldfm_b200.run_bldfm_single(cfg, tower, met_index=mi)
+            assert np.array_equal(single["conc"], r["conc"]) and np.array_equal(single["flx"], r["flx"])
+
+
+def test_timeseries_full_output_and_cache(gpu_lib, oracle, tmp_path, monkeypatch):
+    import bldfm_b200
+    monkeypatch.chdir(tmp_path)
+    cfg = _config(footprint=True, precision="single", full_output=True)
+    cfg.parallel.use_cache = True
+    r1 = bldfm_b200.run_bldfm_timeseries(cfg, cfg.towers[1])
+    assert len(list((tmp_path / ".bldfm_cache").glob("*.npz"))) == 4
+    r2 = bldfm_b200.run_bldfm_timeseries(cfg, cfg.towers[1])
+    for a, b in zip(r1, r2):
+        assert a["conc"].shape == (17, 48, 64)
+        assert np.array_equal(a["conc"], b["conc"]) and np.array_equal(a["flx"], b["flx"])
+    _, oc, of = _oracle_result(oracle, cfg, cfg.towers[1], 2)
+    assert rel_l2(r1[2]["conc"], oc) <= 1e-5 and rel_l2(r1[2]["flx"], of) <= 1e-5
+
+
+def test_parallel_without_process_group_equals_multitower(gpu_lib):
+    import bldfm_b200
+    cfg = _config()
+    a = bldfm_b200.run_bldfm_parallel(cfg, max_workers=4, parallel_over="both")
+    b = bldfm_b200.run_bldfm_multitower(cfg)
+    for name in a:
+        for ra, rb in zip(a[name], b[name]):
+            assert np.array_equal(ra["flx"], rb["flx"])
+    with pytest.raises(ValueError, match="Unknown parallel_over"):
+        bldfm_b200.run_bldfm_parallel(cfg, parallel_over="nope")
+
+
+def test_batch_shares_marches_between_towers(gpu_lib):
+    """8 towers at one height and one met step: one march, eight phase shifts."""
+    import bldfm_b200
+    from bldfm_b200.pbl_model import vertical_profiles
+    z, prof = vertical_profiles(16, 10.0, (3.0, -2.0), ustar=0.4, mol=-60.0)
+    pts = [(100.0 + 90.0 * i, 700.0 - 70.0 * i) for i in range(8)]
+    kw = dict(domain=(960.0, 960.0), levels=16, modes=(64, 64), footprint=True, precision="double")
+    conc, flx = bldfm_b200.solve_batched(np.zeros((64, 64)), [z] * 8, [prof] * 8, meas_pts=pts, **kw)
+    for i, pt in enumerate(pts):
+        _, c1, f1 = bldfm_b200.steady_state_transport_solver(np.zeros((64, 64)), z, prof, meas_pt=pt, **kw)
+        assert np.array_equal(conc[i, 0], c1) and np.array_equal(flx[i, 0], f1)
