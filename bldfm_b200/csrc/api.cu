@@ -275,21 +275,33 @@ int ensure_twiddles(bldfm_plan* pl, bool f32, PrunedFftTables* tab)
     const bldfm_geometry& g = pl->g;
     DevBuf& buf = f32 ? pl->tw32 : pl->tw64;
     const size_t esz = f32 ? sizeof(float2) : sizeof(double2);
+    const size_t tw_bytes = ((size_t)g.nfx + g.nfy) * esz;
     if (!buf.p) {
         std::vector<double> tx, ty;
         fft_twiddles(g.nfx, tx);
         fft_twiddles(g.nfy, ty);
         tx.insert(tx.end(), ty.begin(), ty.end());
-        TRY(buf.ensure(((size_t)g.nfx + g.nfy) * esz));
+        std::vector<int> rx, ry;
+        std::vector<int32_t> vx, vy;
+        fft_factorize(g.nfx, rx);
+        fft_factorize(g.nfy, ry);
+        fft_rev_table(g.nfx, rx, vx);
+        fft_rev_table(g.nfy, ry, vy);
+        vx.insert(vx.end(), vy.begin(), vy.end());
+        TRY(buf.ensure(tw_bytes + vx.size() * sizeof(int32_t)));
         if (f32) {
             std::vector<float> tf(tx.begin(), tx.end());
             CUDA_TRY(cudaMemcpy(buf.p, tf.data(), tf.size() * sizeof(float), cudaMemcpyHostToDevice));
         } else {
             CUDA_TRY(cudaMemcpy(buf.p, tx.data(), tx.size() * sizeof(double), cudaMemcpyHostToDevice));
         }
+        CUDA_TRY(cudaMemcpy(static_cast<char*>(buf.p) + tw_bytes, vx.data(), vx.size() * sizeof(int32_t),
+                            cudaMemcpyHostToDevice));
     }
     tab->tw_x = buf.p;
     tab->tw_y = static_cast<const char*>(buf.p) + (size_t)g.nfx * esz;
+    tab->rev_x = reinterpret_cast<const int32_t*>(static_cast<const char*>(buf.p) + tw_bytes);
+    tab->rev_y = tab->rev_x + g.nfx;
     return BLDFM_OK;
 }
 

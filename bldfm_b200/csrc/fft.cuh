@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/bldfm_b200.h"
@@ -25,13 +26,14 @@
 namespace bldfm {
 
 constexpr int kFftMaxStages = 12;
-constexpr int kFftThreads = 256;
+constexpr int kFftMaxThreads = 384;
 constexpr int kFftPad = 2;   // elements of padding between the transforms of one CTA
 
 struct FftPassArgs {
     int32_t N;                 // transform length
     int32_t nstages;
     int32_t radix[kFftMaxStages];
+    int32_t lshift[kFftMaxStages];   // log2 of the sub-transform length L entering stage s, or -1
     // inputs : in_freq ? n_in entries in fftfreq order (0..(n-1)/2, -(n/2)..-1)
     //                    : a window [in_off, in_off + n_in) ; everything else is zero
     // outputs: out_freq ? n_out entries in fftfreq order : the window [out_off, out_off + n_out)
@@ -49,7 +51,13 @@ struct FftPassArgs {
     void* out;
     void* out2;
     const void* twiddle;       // [N] complex of the compute type: exp(-2*pi*i*k/N)
+    const int32_t* rev;        // [N] natural index -> slot in the digit-reversed DIT layout
 };
+
+// XOR swizzle of the 16-byte element index inside one transform: keeps every access pattern of the
+// DIT stages (stride-1 in j for L >= 8, stride-8 blocks for L = 1) free of shared-memory bank
+// conflicts; it permutes elements only within aligned groups of eight.
+__device__ __forceinline__ int fft_swz(int i) { return i ^ ((i >> 3) & 7); }
 
 template <typename T> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
@@ -139,26 +147,45 @@ template <typename T> __device__ __forceinline__ void bfly8(Cplx<T>* v)
 
 template <typename T, int R>
 __device__ __forceinline__ void fft_stage(typename Vec2<T>::type* buf, const typename Vec2<T>::type* __restrict__ tw,
-                                          int N, int L, int cw)
+                                          int N, int L, int lshift, int cw, int keep_lo, int keep_hi)
 {
     using V = typename Vec2<T>::type;
     const int nbf = N / R;           // butterflies per transform
     const int step = N / (L * R);    // twiddle stride
-    const int total = nbf * cw;
-    for (int b = threadIdx.x; b < total; b += kFftThreads) {
-        const int t = b / nbf;
-        const int jj = b - t * nbf;
-        const int blk = jj / L;
-        const int j = jj - blk * L;
-        V* p = buf + (size_t)t * (N + kFftPad) + (size_t)blk * L * R + j;
+    int t = threadIdx.x / nbf;
+    int jj = threadIdx.x - t * nbf;
+    while (t < cw) {
+        int blk, j;
+        if (lshift >= 0) { blk = jj >> lshift; j = jj & (L - 1); }
+        else { blk = (int)((unsigned)jj / (unsigned)L); j = jj - blk * L; }
+        V* p = buf + (size_t)t * (N + kFftPad);
+        const int i0 = blk * L * R + j;
         Cplx<T> v[R];
 #pragma unroll
-        for (int u = 0; u < R; ++u) { const V x = p[u * L]; v[u] = {x.x, x.y}; }
+        for (int u = 0; u < R; ++u) { const V x = p[fft_swz(i0 + u * L)]; v[u] = {x.x, x.y}; }
         if (L > 1) {
-#pragma unroll
-            for (int u = 1; u < R; ++u) {
-                const V w = tw[(size_t)j * u * step];
-                v[u] = cmul<T>(v[u], Cplx<T>{w.x, w.y});
+            // w_u = w^u from one table load: w = exp(-2*pi*i*j/(L*R)); squares/products instead of
+            // R-1 dependent global loads (the FP64 pipe has slack here, the load path does not)
+            const V w1v = tw[(size_t)j * step];
+            const Cplx<T> w1 = {w1v.x, w1v.y};
+            if (R == 2) {
+                v[1] = cmul<T>(v[1], w1);
+            } else if (R == 3) {
+                const Cplx<T> w2 = cmul<T>(w1, w1);
+                v[1] = cmul<T>(v[1], w1); v[2] = cmul<T>(v[2], w2);
+            } else if (R == 4) {
+                const Cplx<T> w2 = cmul<T>(w1, w1), w3 = cmul<T>(w2, w1);
+                v[1] = cmul<T>(v[1], w1); v[2] = cmul<T>(v[2], w2); v[3] = cmul<T>(v[3], w3);
+            } else if (R == 5) {
+                const Cplx<T> w2 = cmul<T>(w1, w1), w3 = cmul<T>(w2, w1), w4 = cmul<T>(w2, w2);
+                v[1] = cmul<T>(v[1], w1); v[2] = cmul<T>(v[2], w2); v[3] = cmul<T>(v[3], w3);
+                v[4] = cmul<T>(v[4], w4);
+            } else {
+                const Cplx<T> w2 = cmul<T>(w1, w1), w3 = cmul<T>(w2, w1), w4 = cmul<T>(w2, w2);
+                const Cplx<T> w5 = cmul<T>(w4, w1), w6 = cmul<T>(w4, w2), w7 = cmul<T>(w4, w3);
+                v[1] = cmul<T>(v[1], w1); v[2] = cmul<T>(v[2], w2); v[3] = cmul<T>(v[3], w3);
+                v[4] = cmul<T>(v[4], w4); v[5] = cmul<T>(v[5], w5); v[6] = cmul<T>(v[6], w6);
+                v[7] = cmul<T>(v[7], w7);
             }
         }
         if (R == 2) bfly2<T>(v);
@@ -167,28 +194,18 @@ __device__ __forceinline__ void fft_stage(typename Vec2<T>::type* buf, const typ
         else if (R == 5) bfly5<T>(v);
         else bfly8<T>(v);
 #pragma unroll
-        for (int u = 0; u < R; ++u) p[u * L] = mk2<T>(v[u].r, v[u].i);
+        for (int u = 0; u < R; ++u) {
+            const int i = i0 + u * L;
+            if (i >= keep_lo && i < keep_hi) p[fft_swz(i)] = mk2<T>(v[u].r, v[u].i);
+        }
+        jj += (int)blockDim.x;
+        while (jj >= nbf) { jj -= nbf; ++t; }
     }
 }
 
-// position of natural input index i in the digit-reversed DIT layout
-__device__ __forceinline__ int fft_digit_reverse(int i, const FftPassArgs& a)
-{
-    int pos = 0, ncur = a.N;
-    for (int s = a.nstages - 1; s >= 0; --s) {
-        const int r = a.radix[s];
-        const int q = i / r;
-        const int d = i - q * r;
-        ncur /= r;
-        pos += d * ncur;
-        i = q;
-    }
-    return pos;
-}
-
-// grid = (ceil(ntrans/cw), nfields) ; block = kFftThreads ; dynamic smem = cw*(N+pad)*sizeof(complex)
+// grid = (ceil(ntrans/cw), nfields) ; block = fft_pick_threads() ; dynamic smem = cw*(N+pad)*sizeof(complex)
 template <typename T, bool REAL_IN, bool REAL_OUT>
-__global__ void __launch_bounds__(kFftThreads)
+__global__ void __launch_bounds__(kFftMaxThreads, 2)
 k_fft_pass(const FftPassArgs a)
 {
     using V = typename Vec2<T>::type;
@@ -204,10 +221,10 @@ k_fft_pass(const FftPassArgs a)
     const T sgn = a.conj_io ? (T)-1 : (T)1;
 
     // zero fill, then scatter the non-zero inputs to their digit-reversed slots
-    for (int e = threadIdx.x; e < cw * (N + kFftPad); e += kFftThreads) buf[e] = mk2<T>((T)0, (T)0);
+    for (int e = threadIdx.x; e < cw * (N + kFftPad); e += (int)blockDim.x) buf[e] = mk2<T>((T)0, (T)0);
     __syncthreads();
     const int npos_in = (a.n_in + 1) / 2;
-    for (int e = threadIdx.x; e < cw * a.n_in; e += kFftThreads) {
+    for (int e = threadIdx.x; e < cw * a.n_in; e += (int)blockDim.x) {
         int t, k;
         if (a.t_fast) { k = e / cw; t = e - k * cw; }
         else          { t = e / a.n_in; k = e - t * a.n_in; }
@@ -216,7 +233,7 @@ k_fft_pass(const FftPassArgs a)
         T xr, xi;
         if (REAL_IN) { xr = reinterpret_cast<const T*>(inp)[g]; xi = (T)0; }
         else { const V x = reinterpret_cast<const V*>(inp)[g]; xr = x.x; xi = x.y; }
-        buf[(size_t)t * (N + kFftPad) + fft_digit_reverse(i, a)] = mk2<T>(xr, sgn * xi);
+        buf[(size_t)t * (N + kFftPad) + fft_swz(a.rev[i])] = mk2<T>(xr, sgn * xi);
     }
     __syncthreads();
 
@@ -224,12 +241,15 @@ k_fft_pass(const FftPassArgs a)
     int L = 1;
     for (int s = 0; s < a.nstages; ++s) {
         const int r = a.radix[s];
+        // the last stage only needs to keep what the output window will read
+        const bool last = (s == a.nstages - 1) && !a.out_freq;
+        const int lo = last ? a.out_off : 0, hi = last ? a.out_off + a.n_out : N;
         switch (r) {
-            case 2: fft_stage<T, 2>(buf, tw, N, L, cw); break;
-            case 3: fft_stage<T, 3>(buf, tw, N, L, cw); break;
-            case 4: fft_stage<T, 4>(buf, tw, N, L, cw); break;
-            case 5: fft_stage<T, 5>(buf, tw, N, L, cw); break;
-            default: fft_stage<T, 8>(buf, tw, N, L, cw); break;
+            case 2: fft_stage<T, 2>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
+            case 3: fft_stage<T, 3>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
+            case 4: fft_stage<T, 4>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
+            case 5: fft_stage<T, 5>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
+            default: fft_stage<T, 8>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
         }
         L *= r;
         __syncthreads();
@@ -237,12 +257,12 @@ k_fft_pass(const FftPassArgs a)
 
     // store the requested outputs
     const int npos_out = (a.n_out + 1) / 2;
-    for (int e = threadIdx.x; e < cw * a.n_out; e += kFftThreads) {
+    for (int e = threadIdx.x; e < cw * a.n_out; e += (int)blockDim.x) {
         int t, j;
         if (a.t_fast) { j = e / cw; t = e - j * cw; }
         else          { t = e / a.n_out; j = e - t * a.n_out; }
         const int i = a.out_freq ? (j < npos_out ? j : j - a.n_out + N) : a.out_off + j;
-        const V x = buf[(size_t)t * (N + kFftPad) + i];
+        const V x = buf[(size_t)t * (N + kFftPad) + fft_swz(i)];
         const size_t o = field * a.out_field_stride + (size_t)(t0 + t) * a.out_tstride +
                          (size_t)j * a.out_jstride;
         if (REAL_OUT) reinterpret_cast<T*>(outp)[o] = x.x;
@@ -257,18 +277,48 @@ inline bool fft_factorize(int n, std::vector<int>& radix)
 {
     radix.clear();
     if (n < 1) return false;
-    std::vector<int> small;   // 3s and 5s first (keeps the power-of-two stages' strides aligned)
-    while (n % 3 == 0) { small.push_back(3); n /= 3; }
-    while (n % 5 == 0) { small.push_back(5); n /= 5; }
-    std::vector<int> pow2;
+    // powers of two first: the sub-transform length L stays a power of two (shift/mask indexing)
+    // until the 3s and 5s come in at the end.
+    std::vector<int> pow2, odd;
     while (n % 8 == 0) { pow2.push_back(8); n /= 8; }
     while (n % 4 == 0) { pow2.push_back(4); n /= 4; }
     while (n % 2 == 0) { pow2.push_back(2); n /= 2; }
+    while (n % 3 == 0) { odd.push_back(3); n /= 3; }
+    while (n % 5 == 0) { odd.push_back(5); n /= 5; }
     if (n != 1) return false;
-    radix = small;
-    radix.insert(radix.end(), pow2.begin(), pow2.end());
-    if (radix.empty()) radix.push_back(1);
-    return (int)radix.size() <= kFftMaxStages;
+    radix = pow2;
+    radix.insert(radix.end(), odd.begin(), odd.end());
+    return !radix.empty() && (int)radix.size() <= kFftMaxStages;
+}
+
+// fills radix[], lshift[] of a pass
+inline void fft_set_stages(FftPassArgs& a, const std::vector<int>& radix)
+{
+    a.nstages = (int)radix.size();
+    int L = 1;
+    for (size_t i = 0; i < radix.size(); ++i) {
+        a.radix[i] = radix[i];
+        int sh = -1;
+        if ((L & (L - 1)) == 0) { sh = 0; while ((1 << sh) < L) ++sh; }
+        a.lshift[i] = sh;
+        L *= radix[i];
+    }
+}
+
+// rev[i] = slot of natural input index i in the digit-reversed layout of the DIT stages
+inline void fft_rev_table(int N, const std::vector<int>& radix, std::vector<int32_t>& rev)
+{
+    rev.resize((size_t)N);
+    for (int i0 = 0; i0 < N; ++i0) {
+        int i = i0, pos = 0, ncur = N;
+        for (int s = (int)radix.size() - 1; s >= 0; --s) {
+            const int r = radix[(size_t)s];
+            ncur /= r;
+            pos += (i % r) * ncur;
+            i /= r;
+        }
+        rev[(size_t)i0] = pos;
+    }
 }
 
 inline size_t fft_smem_bytes(int N, int cw, bool f32)
@@ -276,12 +326,33 @@ inline size_t fft_smem_bytes(int N, int cw, bool f32)
     return (size_t)cw * (size_t)(N + kFftPad) * (f32 ? sizeof(float2) : sizeof(double2));
 }
 
+inline int fft_env_int(const char* name, int dflt)
+{
+    const char* v = std::getenv(name);
+    return (v && *v) ? std::atoi(v) : dflt;
+}
+
 // transforms per CTA for the two passes given the shared-memory budget
 inline int fft_pick_cw(int N, bool f32, size_t smem_optin, int want)
 {
-    int cw = want;
+    int cw = fft_env_int("BLDFM_FFT_CW", want);
     while (cw > 1 && fft_smem_bytes(N, cw, f32) > smem_optin / 2) cw /= 2;   // keep >= 2 CTAs / SM
     return cw;
+}
+
+// threads per CTA: the widest stage (largest radix first) has cw*N/r butterflies; give each thread
+// a whole number of them where possible
+inline int fft_pick_threads(int N, int cw, int r0)
+{
+    const int forced = fft_env_int("BLDFM_FFT_THREADS", 0);
+    if (forced > 0) return std::min(kFftMaxThreads, std::max(32, forced / 32 * 32));
+    const int nb = cw * (N / std::max(r0, 1));
+    int best = 256;
+    for (int t : {384, 256, 320, 192, 128}) {
+        if (t <= nb && nb % t == 0) { best = t; break; }
+    }
+    if (nb < 128) best = std::max(32, (nb + 31) / 32 * 32);
+    return best;
 }
 
 inline bool pruned_fft_supported(const bldfm_geometry& g, bool f32, size_t smem_optin)
@@ -314,6 +385,8 @@ inline void fft_twiddles(int N, std::vector<double>& out)
 struct PrunedFftTables {
     const void* tw_x = nullptr;   // device, compute type
     const void* tw_y = nullptr;
+    const int32_t* rev_x = nullptr;
+    const int32_t* rev_y = nullptr;
 };
 
 // Runs both passes for the `nfields` compact spectra of spec_p (-> out_p) and of spec_q (-> out_q)
@@ -331,8 +404,7 @@ inline cudaError_t pruned_fft_launch(cudaStream_t stream, size_t smem_optin, con
     fft_factorize(g.nfy, ry);
 
     FftPassArgs ax{};
-    ax.N = g.nfx; ax.nstages = (int)rx.size();
-    for (size_t i = 0; i < rx.size(); ++i) ax.radix[i] = rx[i];
+    ax.N = g.nfx; fft_set_stages(ax, rx); ax.rev = tab.rev_x;
     ax.in_freq = 1; ax.n_in = g.nlx; ax.in_off = 0; ax.out_freq = 0; ax.n_out = g.nx; ax.out_off = g.px;
     ax.cw = fft_pick_cw(g.nfx, f32, smem_optin, 4);
     ax.ntrans = g.nly; ax.t_fast = 0; ax.conj_io = forward_dir ? 0 : 1;
@@ -341,8 +413,7 @@ inline cudaError_t pruned_fft_launch(cudaStream_t stream, size_t smem_optin, con
     ax.twiddle = tab.tw_x;
 
     FftPassArgs ay{};
-    ay.N = g.nfy; ay.nstages = (int)ry.size();
-    for (size_t i = 0; i < ry.size(); ++i) ay.radix[i] = ry[i];
+    ay.N = g.nfy; fft_set_stages(ay, ry); ay.rev = tab.rev_y;
     ay.in_freq = 1; ay.n_in = g.nly; ay.in_off = 0; ay.out_freq = 0; ay.n_out = g.ny; ay.out_off = g.py;
     ay.cw = fft_pick_cw(g.nfy, f32, smem_optin, 4);
     ay.ntrans = g.nx; ay.t_fast = 1; ay.conj_io = forward_dir ? 0 : 1;
@@ -370,8 +441,10 @@ inline cudaError_t pruned_fft_launch(cudaStream_t stream, size_t smem_optin, con
         by.in = bx.out; by.in2 = bx.out2;
         by.out = reinterpret_cast<T*>(out_p) + (size_t)f0 * ay.out_field_stride;
         by.out2 = reinterpret_cast<T*>(out_q) + (size_t)f0 * ay.out_field_stride;
-        k_fft_pass<T, false, false><<<dim3((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), (unsigned)(2 * nf)), kFftThreads, sx, stream>>>(bx);
-        k_fft_pass<T, false, true><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), (unsigned)(2 * nf)), kFftThreads, sy, stream>>>(by);
+        k_fft_pass<T, false, false><<<dim3((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), (unsigned)(2 * nf)),
+                                      fft_pick_threads(ax.N, ax.cw, ax.radix[0]), sx, stream>>>(bx);
+        k_fft_pass<T, false, true><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), (unsigned)(2 * nf)),
+                                     fft_pick_threads(ay.N, ay.cw, ay.radix[0]), sy, stream>>>(by);
         *nlaunch += 2;
     }
     return cudaGetLastError();
@@ -388,8 +461,7 @@ inline cudaError_t pruned_fft_forward(cudaStream_t stream, size_t smem_optin, co
     fft_factorize(g.nxe, rx);
     fft_factorize(g.nye, ry);
     FftPassArgs ax{};
-    ax.N = g.nxe; ax.nstages = (int)rx.size();
-    for (size_t i = 0; i < rx.size(); ++i) ax.radix[i] = rx[i];
+    ax.N = g.nxe; fft_set_stages(ax, rx); ax.rev = tab.rev_x;
     ax.in_freq = 0; ax.n_in = g.nx; ax.in_off = g.px; ax.out_freq = 1; ax.n_out = g.nlx; ax.out_off = 0;
     ax.cw = fft_pick_cw(g.nxe, false, smem_optin, 4);
     ax.ntrans = g.ny; ax.t_fast = 0; ax.conj_io = 0;
@@ -398,8 +470,7 @@ inline cudaError_t pruned_fft_forward(cudaStream_t stream, size_t smem_optin, co
     ax.nfields_first = 1; ax.in = q0; ax.in2 = q0; ax.out = work; ax.out2 = work; ax.twiddle = tab.tw_x;
 
     FftPassArgs ay{};
-    ay.N = g.nye; ay.nstages = (int)ry.size();
-    for (size_t i = 0; i < ry.size(); ++i) ay.radix[i] = ry[i];
+    ay.N = g.nye; fft_set_stages(ay, ry); ay.rev = tab.rev_y;
     ay.in_freq = 0; ay.n_in = g.ny; ay.in_off = g.py; ay.out_freq = 1; ay.n_out = g.nly; ay.out_off = 0;
     ay.cw = fft_pick_cw(g.nye, false, smem_optin, 4);
     ay.ntrans = g.nlx; ay.t_fast = 1; ay.conj_io = 0;
@@ -412,9 +483,11 @@ inline cudaError_t pruned_fft_forward(cudaStream_t stream, size_t smem_optin, co
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_fft_pass<double, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
     if (e != cudaSuccess) return e;
-    k_fft_pass<double, true, false><<<dim3((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), 1), kFftThreads,
+    k_fft_pass<double, true, false><<<dim3((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), 1),
+                                      fft_pick_threads(ax.N, ax.cw, ax.radix[0]),
                                       fft_smem_bytes(ax.N, ax.cw, false), stream>>>(ax);
-    k_fft_pass<double, false, false><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), 1), kFftThreads,
+    k_fft_pass<double, false, false><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), 1),
+                                       fft_pick_threads(ay.N, ay.cw, ay.radix[0]),
                                        fft_smem_bytes(ay.N, ay.cw, false), stream>>>(ay);
     *nlaunch += 2;
     return cudaGetLastError();
