@@ -314,8 +314,18 @@ struct SolveOut {
     double* tfftq = nullptr;
 };
 
+// ky-slab sharding of one oversized problem: this rank marches rows
+// [rank*nly/G, (rank+1)*nly/G) and x-transforms them into per-destination blocks.
+struct Shard {
+    int rank = 0, nranks = 1;
+    void* send_p = nullptr;            // [field][dst][rows][nx/G] complex128 (device)
+    void* send_q = nullptr;
+    void* const* peer_p = nullptr;     // optional device arrays of G peer pointers (fused transpose)
+    void* const* peer_q = nullptr;
+};
+
 int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int64_t* levels,
-               int nlv, const double* srf_flx, int flags, const SolveOut& out)
+               int nlv, const double* srf_flx, int flags, const SolveOut& out, const Shard* sh = nullptr)
 {
     if (!pl) return fail(BLDFM_ERR_INVALID, "plan is NULL");
     if (nprob < 1 || !probs) return fail(BLDFM_ERR_INVALID, "no problems given");
@@ -332,6 +342,20 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         return fail(BLDFM_ERR_ODD_PAD, "padded grid size minus modes must be even.");
     if (analytic && nlv != 1)
         return fail(BLDFM_ERR_ANALYTIC_LEVELS, "analytic=True supports a single output level.");
+
+    int ky0 = 0, rows = g.nly;
+    if (sh) {
+        if (nprob != 1) return fail(BLDFM_ERR_INVALID, "sharded solve takes one problem");
+        if (!footprint) return fail(BLDFM_ERR_INVALID, "sharded solve supports footprint mode only (non-footprint: not built yet)");
+        if (sh->nranks < 1 || sh->rank < 0 || sh->rank >= sh->nranks) return fail(BLDFM_ERR_INVALID, "bad rank / nranks");
+        if (g.nly % sh->nranks || g.nx % sh->nranks)
+            return fail(BLDFM_ERR_INVALID, "sharded solve needs nly and nx divisible by the number of ranks");
+        if (!pruned_fft_supported(g, false, pl->smem_optin))
+            return fail(BLDFM_ERR_INVALID, "sharded solve needs the in-house transform (size factors 2,3,5; <= 227 KB shared memory)");
+        if (!sh->send_p || !sh->send_q) return fail(BLDFM_ERR_INVALID, "send buffers are NULL");
+        rows = g.nly / sh->nranks;
+        ky0 = sh->rank * rows;
+    }
 
     DeviceGuard guard(pl->device);
     if (!guard.ok) return fail(BLDFM_ERR_CUDA, "cudaSetDevice failed");
@@ -403,7 +427,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     if (!dbl && n_shift != 0 && n_shift != nprob)
         return fail(BLDFM_ERR_INVALID, "precision='single' batch mixes shifted and unshifted meas_pt (float32/float64 outputs)");
     const bool out_f32 = !dbl && n_shift == 0;
-    const bool spec_f32 = out_f32 && !spectral;
+    const bool spec_f32 = out_f32 && !spectral && !sh;
     const size_t celem = spec_f32 ? sizeof(float2) : sizeof(double2);
     const size_t relem = out_f32 ? sizeof(float) : sizeof(double);
 
@@ -491,7 +515,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev[1], pl->stream));
 
     // ---- K4-K8: fused march -> compact spectra
-    const int64_t nmodes = (int64_t)g.nlx * g.nly;
+    const int64_t nmodes = (int64_t)g.nlx * rows;
     const int64_t nfields = (int64_t)nprob * nlv;
     TRY(pl->spec_p.ensure((size_t)nfields * nmodes * celem));
     TRY(pl->spec_q.ensure((size_t)nfields * nmodes * celem));
@@ -499,6 +523,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         char* dbase = static_cast<char*>(pl->params.p);
         MarchArgs a{};
         a.nlx = g.nlx; a.nly = g.nly; a.nlv = nlv;
+        a.ky0 = ky0; a.nly_loc = rows;
         a.coef_stride = coef_stride; a.nrow_of = nz_max;
         a.snap_level = lp.snap_level; a.last_level = lp.last_level;
         a.single = dbl ? 0 : 1;
@@ -542,6 +567,24 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         pl->launches++;
     }
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev[2], pl->stream));
+
+    if (sh) {
+        PrunedFftTables tab;
+        TRY(ensure_twiddles(pl, false, &tab));
+        int nl = 0;
+        cudaError_t fe = sharded_xpass(pl->stream, pl->smem_optin, g, footprint, rows, sh->nranks, pl->spec_p.p,
+                                       pl->spec_q.p, (int)nfields, sh->send_p, sh->send_q, sh->peer_p, sh->peer_q,
+                                       (int64_t)g.nly * (g.nx / sh->nranks), tab, &nl);
+        if (fe != cudaSuccess) return fail(BLDFM_ERR_CUDA, std::string("sharded x-pass: ") + cudaGetErrorString(fe));
+        pl->launches += nl;
+        if (pl->profiling) {
+            CUDA_TRY(cudaEventRecord(pl->ev[3], pl->stream));
+            CUDA_TRY(cudaEventRecord(pl->ev[4], pl->stream));
+            pl->ev_recorded = true;
+        }
+        if (!(flags & BLDFM_ASYNC)) CUDA_TRY(cudaStreamSynchronize(pl->stream));
+        return BLDFM_OK;
+    }
 
     if (spectral) {
         // parity export of tfftp/tfftq before solver.py:265
@@ -856,6 +899,68 @@ int bldfm_solve_spectral(bldfm_plan* plan, const bldfm_problem* prob, const int6
     if (!tfftp || !tfftq) return fail(BLDFM_ERR_INVALID, "output pointer is NULL");
     SolveOut o; o.tfftp = tfftp; o.tfftq = tfftq;
     return solve_impl(plan, 1, prob, levels, nlv, srf_flx, flags, o);
+}
+
+int bldfm_sharded_stage1(bldfm_plan* plan, const bldfm_problem* prob, const int64_t* levels, int32_t nlv,
+                         int flags, int32_t rank, int32_t nranks, void* send_p, void* send_q,
+                         void* const* peer_p, void* const* peer_q)
+{
+    Shard sh;
+    sh.rank = rank; sh.nranks = nranks; sh.send_p = send_p; sh.send_q = send_q;
+    sh.peer_p = peer_p; sh.peer_q = peer_q;
+    SolveOut o;
+    return solve_impl(plan, 1, prob, levels, nlv, nullptr, flags | BLDFM_OUT_ON_DEVICE, o, &sh);
+}
+
+int bldfm_sharded_stage2(bldfm_plan* pl, int32_t nlv, int flags, int32_t rank, int32_t nranks,
+                         const void* recv_p, const void* recv_q, void* conc_slab, void* flx_slab)
+{
+    (void)rank;
+    if (!pl || !recv_p || !recv_q || !conc_slab || !flx_slab) return fail(BLDFM_ERR_INVALID, "NULL argument");
+    const bldfm_geometry& g = pl->g;
+    if (nranks < 1 || g.nly % nranks || g.nx % nranks)
+        return fail(BLDFM_ERR_INVALID, "sharded solve needs nly and nx divisible by the number of ranks");
+    if (!pruned_fft_supported(g, false, pl->smem_optin))
+        return fail(BLDFM_ERR_INVALID, "sharded solve needs the in-house transform");
+    DeviceGuard guard(pl->device);
+    if (!guard.ok) return fail(BLDFM_ERR_CUDA, "cudaSetDevice failed");
+    PrunedFftTables tab;
+    TRY(ensure_twiddles(pl, false, &tab));
+    int nl = 0;
+    cudaError_t fe = sharded_ypass(pl->stream, pl->smem_optin, g, (flags & BLDFM_FOOTPRINT) != 0, nranks, recv_p,
+                                   recv_q, nlv, conc_slab, flx_slab, tab, &nl);
+    if (fe != cudaSuccess) return fail(BLDFM_ERR_CUDA, std::string("sharded y-pass: ") + cudaGetErrorString(fe));
+    pl->launches += nl;
+    if (!(flags & BLDFM_ASYNC)) CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return BLDFM_OK;
+}
+
+int bldfm_ipc_export(void* dev_ptr, unsigned char* handle64)
+{
+    if (!dev_ptr || !handle64) return fail(BLDFM_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle64, &h, 64);
+    return BLDFM_OK;
+}
+
+int bldfm_ipc_open(int device, const unsigned char* handle64, void** out)
+{
+    if (!handle64 || !out) return fail(BLDFM_ERR_INVALID, "NULL argument");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(BLDFM_ERR_CUDA, "cudaSetDevice failed");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CUDA_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return BLDFM_OK;
+}
+
+int bldfm_ipc_close(int device, void* p)
+{
+    DeviceGuard guard(device);
+    if (p) CUDA_TRY(cudaIpcCloseMemHandle(p));
+    return BLDFM_OK;
 }
 
 int bldfm_march(int device, int64_t M, const double* p0, const double* q0, int32_t nz,

@@ -45,6 +45,11 @@ struct FftPassArgs {
     int32_t conj_io;           // 1: inverse transform through conj(FFT(conj(x)))
     int64_t in_field_stride, in_tstride, in_kstride;      // in elements
     int64_t out_field_stride, out_tstride, out_jstride;   // in elements
+    // optional blocking of the output index j (ky-slab sharding: one block per destination rank):
+    // offset = (j / out_block) * out_block_stride + (j % out_block) * out_jstride ; out_block = 0: off
+    int32_t out_block;
+    int64_t out_block_stride;
+    void* const* out_peer;     // optional [n blocks] base pointers (peer GPUs); overrides `out`
     int32_t nfields_first;     // fields [0, nfields_first) use in/out, the rest in2/out2
     const void* in;
     const void* in2;
@@ -263,10 +268,19 @@ k_fft_pass(const FftPassArgs a)
         else          { t = e / a.n_out; j = e - t * a.n_out; }
         const int i = a.out_freq ? (j < npos_out ? j : j - a.n_out + N) : a.out_off + j;
         const V x = buf[(size_t)t * (N + kFftPad) + fft_swz(i)];
-        const size_t o = field * a.out_field_stride + (size_t)(t0 + t) * a.out_tstride +
-                         (size_t)j * a.out_jstride;
-        if (REAL_OUT) reinterpret_cast<T*>(outp)[o] = x.x;
-        else reinterpret_cast<V*>(outp)[o] = mk2<T>(x.x, sgn * x.y);
+        size_t o = field * a.out_field_stride + (size_t)(t0 + t) * a.out_tstride;
+        void* dst = outp;
+        if (a.out_block > 0) {
+            const int blk = j / a.out_block;
+            const int jb = j - blk * a.out_block;
+            if (a.out_peer) dst = a.out_peer[blk];
+            else o += (size_t)blk * a.out_block_stride;
+            o += (size_t)jb * a.out_jstride;
+        } else {
+            o += (size_t)j * a.out_jstride;
+        }
+        if (REAL_OUT) reinterpret_cast<T*>(dst)[o] = x.x;
+        else reinterpret_cast<V*>(dst)[o] = mk2<T>(x.x, sgn * x.y);
     }
 }
 
@@ -447,6 +461,86 @@ inline cudaError_t pruned_fft_launch(cudaStream_t stream, size_t smem_optin, con
                                      fft_pick_threads(ay.N, ay.cw, ay.radix[0]), sy, stream>>>(by);
         *nlaunch += 2;
     }
+    return cudaGetLastError();
+}
+
+// ---- ky-slab sharded back-transform ------------------------------------------------
+// stage 1 (every rank): x-transform of the local rows [ky0, ky0+rows) of each field; the output index
+// x' is blocked by destination rank: send[field][dst][rows][nx/G]  (or written straight into the
+// peers' receive buffers when `peer_p/peer_q` are given -- the transpose then rides on the stores).
+inline cudaError_t sharded_xpass(cudaStream_t stream, size_t smem_optin, const bldfm_geometry& g,
+                                 bool forward_dir, int rows, int nranks, const void* spec_p, const void* spec_q,
+                                 int nfields, void* send_p, void* send_q, void* const* peer_p,
+                                 void* const* peer_q, int64_t peer_field_stride, const PrunedFftTables& tab,
+                                 int* nlaunch)
+{
+    std::vector<int> rx;
+    fft_factorize(g.nfx, rx);
+    const int nxl = g.nx / nranks;
+    FftPassArgs ax{};
+    ax.N = g.nfx; fft_set_stages(ax, rx); ax.rev = tab.rev_x;
+    ax.in_freq = 1; ax.n_in = g.nlx; ax.in_off = 0; ax.out_freq = 0; ax.n_out = g.nx; ax.out_off = g.px;
+    ax.cw = fft_pick_cw(g.nfx, false, smem_optin, 4);
+    ax.ntrans = rows; ax.t_fast = 0; ax.conj_io = forward_dir ? 0 : 1;
+    ax.in_field_stride = (int64_t)rows * g.nlx; ax.in_tstride = g.nlx; ax.in_kstride = 1;
+    ax.out_tstride = nxl; ax.out_jstride = 1; ax.out_block = nxl;
+    if (peer_p) {
+        ax.out_field_stride = peer_field_stride;      // receiver layout [field][nly][nx/G]
+        ax.out_block_stride = 0;
+        ax.out_peer = peer_p;
+    } else {
+        ax.out_field_stride = (int64_t)rows * g.nx;   // [field][dst][rows][nx/G]
+        ax.out_block_stride = (int64_t)rows * nxl;
+    }
+    ax.twiddle = tab.tw_x;
+    ax.nfields_first = nfields;
+    ax.in = spec_p; ax.in2 = spec_q; ax.out = send_p; ax.out2 = send_q;
+    cudaError_t e = cudaFuncSetAttribute(k_fft_pass<double, false, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    if (e != cudaSuccess) return e;
+    const dim3 grid((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), (unsigned)nfields);
+    const int th = fft_pick_threads(ax.N, ax.cw, ax.radix[0]);
+    const size_t sm = fft_smem_bytes(ax.N, ax.cw, false);
+    if (peer_p) {
+        // two launches: the p fields then the q fields (each has its own peer pointer table)
+        FftPassArgs a1 = ax; a1.in2 = spec_p; a1.out2 = send_p;
+        k_fft_pass<double, false, false><<<grid, th, sm, stream>>>(a1);
+        FftPassArgs a2 = ax; a2.in = spec_q; a2.in2 = spec_q; a2.out_peer = peer_q;
+        k_fft_pass<double, false, false><<<grid, th, sm, stream>>>(a2);
+        *nlaunch += 2;
+    } else {
+        const dim3 grid2(grid.x, (unsigned)(2 * nfields));
+        k_fft_pass<double, false, false><<<grid2, th, sm, stream>>>(ax);
+        *nlaunch += 1;
+    }
+    return cudaGetLastError();
+}
+
+// stage 2 (every rank): y-transform of the received [field][nly][nx/G] -> real [field][ny][nx/G]
+inline cudaError_t sharded_ypass(cudaStream_t stream, size_t smem_optin, const bldfm_geometry& g,
+                                 bool forward_dir, int nranks, const void* recv_p, const void* recv_q,
+                                 int nfields, void* out_p, void* out_q, const PrunedFftTables& tab, int* nlaunch)
+{
+    std::vector<int> ry;
+    fft_factorize(g.nfy, ry);
+    const int nxl = g.nx / nranks;
+    FftPassArgs ay{};
+    ay.N = g.nfy; fft_set_stages(ay, ry); ay.rev = tab.rev_y;
+    ay.in_freq = 1; ay.n_in = g.nly; ay.in_off = 0; ay.out_freq = 0; ay.n_out = g.ny; ay.out_off = g.py;
+    ay.cw = fft_pick_cw(g.nfy, false, smem_optin, 4);
+    ay.ntrans = nxl; ay.t_fast = 1; ay.conj_io = forward_dir ? 0 : 1;
+    ay.in_field_stride = (int64_t)g.nly * nxl; ay.in_tstride = 1; ay.in_kstride = nxl;
+    ay.out_field_stride = (int64_t)g.ny * nxl; ay.out_tstride = 1; ay.out_jstride = nxl;
+    ay.twiddle = tab.tw_y;
+    ay.nfields_first = nfields;
+    ay.in = recv_p; ay.in2 = recv_q; ay.out = out_p; ay.out2 = out_q;
+    cudaError_t e = cudaFuncSetAttribute(k_fft_pass<double, false, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    if (e != cudaSuccess) return e;
+    k_fft_pass<double, false, true><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), (unsigned)(2 * nfields)),
+                                      fft_pick_threads(ay.N, ay.cw, ay.radix[0]),
+                                      fft_smem_bytes(ay.N, ay.cw, false), stream>>>(ay);
+    *nlaunch += 1;
     return cudaGetLastError();
 }
 

@@ -138,6 +138,7 @@ __device__ __forceinline__ void apply(const Prop& P, double& pr, double& pi, dou
 // ------------------------------------------------------------------------------------------------
 struct MarchArgs {
     int32_t nlx, nly;          // retained modes
+    int32_t ky0, nly_loc;      // this launch covers rows ky0 .. ky0+nly_loc-1 (ky-slab sharding)
     int32_t nlv;               // output rows
     int32_t coef_stride;       // LevelCoef entries per group (= max steps)
     int32_t nrow_of;           // entries in row_of (= max nz)
@@ -157,9 +158,9 @@ struct MarchArgs {
     const TowerDesc* towers;
     const double*    lx;       // [nlx]
     const double*    ly;       // [nly]
-    void* outp;                // [slot][row][nly][nlx] complex (double2 | float2)
+    void* outp;                // [slot][row][nly_loc][nlx] complex (double2 | float2)
     void* outq;
-    int64_t slot_stride;       // complex elements between output slots (= nlv*nly*nlx)
+    int64_t slot_stride;       // complex elements between output slots (= nlv*nly_loc*nlx)
 };
 
 __device__ __forceinline__ double round_f32(double x) { return (double)(float)x; }
@@ -194,7 +195,7 @@ struct Emit {
         if (a.single) {
             pr = round_f32(pr); pi = round_f32(pi); qr = round_f32(qr); qi = round_f32(qi);
         }
-        const int64_t rowoff = (int64_t)row * a.nly * a.nlx + mode;
+        const int64_t rowoff = (int64_t)row * a.nly_loc * a.nlx + mode;
         for (int t = 0; t < gd.tow_count; ++t) {
             const TowerDesc td = tw[t];
             double opr = pr, opi = pi, oqr = qr, oqi = qi;
@@ -220,7 +221,7 @@ constexpr int kMarchThreads = 128;
 
 // grid = (ceil(nlx*nly / kMarchThreads), ngroups) ; dynamic smem = coef_stride*128 + nrow_of*4
 template <bool FMA, bool MULTI>
-__global__ void __launch_bounds__(kMarchThreads)
+__global__ void __launch_bounds__(kMarchThreads, 7)
 k_march(const MarchArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -238,9 +239,10 @@ k_march(const MarchArgs a)
     __syncthreads();
 
     const int64_t mode = (int64_t)blockIdx.x * kMarchThreads + threadIdx.x;
-    if (mode >= (int64_t)a.nlx * a.nly) return;
-    const int ky = (int)(mode / a.nlx);
-    const int kx = (int)(mode - (int64_t)ky * a.nlx);
+    if (mode >= (int64_t)a.nlx * a.nly_loc) return;
+    const int kyl = (int)(mode / a.nlx);
+    const int kx = (int)(mode - (int64_t)kyl * a.nlx);
+    const int ky = a.ky0 + kyl;
     const double lx = a.lx[kx], ly = a.ly[ky];
 
     // source spectrum of this mode (solver.py:134 / :136-145)
@@ -257,7 +259,7 @@ k_march(const MarchArgs a)
 
     const Emit emit(a, gd, mode, lx, ly);
 
-    if (mode == 0) {
+    if (ky == 0 && kx == 0) {
         // degenerate mode: flux constant, concentration by the trapezoid rule (solver.py:190-191,239-251)
         double pr = gd.p000, pi = 0.0;
         bool any = false;
@@ -369,9 +371,10 @@ k_analytic(const MarchArgs a)
 {
     const GroupDesc gd = a.groups[blockIdx.y];
     const int64_t mode = (int64_t)blockIdx.x * kMarchThreads + threadIdx.x;
-    if (mode >= (int64_t)a.nlx * a.nly) return;
-    const int ky = (int)(mode / a.nlx);
-    const int kx = (int)(mode - (int64_t)ky * a.nlx);
+    if (mode >= (int64_t)a.nlx * a.nly_loc) return;
+    const int kyl = (int)(mode / a.nlx);
+    const int kx = (int)(mode - (int64_t)kyl * a.nlx);
+    const int ky = a.ky0 + kyl;
     const double lx = a.lx[kx], ly = a.ly[ky];
     double q0r, q0i;
     if (a.footprint) {
@@ -385,7 +388,7 @@ k_analytic(const MarchArgs a)
     }
     const Emit emit(a, gd, mode, lx, ly);
     const double h = gd.h_analytic;
-    if (mode == 0) {
+    if (ky == 0 && kx == 0) {
         // tfftp[:,0,0] = p000 - tfftq0[0,0]*Kzinv*h ; tfftq[:,0,0] = tfftq0[0,0]
         const double pr = gd.p000 - (q0r * gd.kinv_top) * h;
         const double pi = 0.0 - (q0i * gd.kinv_top) * h;

@@ -133,6 +133,27 @@ int  bldfm_solve_batched(bldfm_plan *plan, int32_t nprob, const bldfm_problem *p
                          const int64_t *levels, int32_t nlv, const double *srf_flx, int flags,
                          void *conc, void *flx);
 
+/* One OVERSIZED problem sharded by ky-slab over `nranks` GPUs (one process per GPU); replaces nothing
+ * in the reference -- it scales a single steady_state_transport_solver call (src/bldfm/solver.py:16)
+ * beyond one device.  Footprint mode, float64.  Every rank calls
+ *   stage1: march + x-transform of the retained rows [rank*nly/G, (rank+1)*nly/G); results go to the
+ *           device buffers send_p/send_q laid out [nlv][dst][nly/G][nx/G] complex128, ready for an
+ *           all-to-all (done by the caller, e.g. torch.distributed over NCCL) -- or, when peer_p/peer_q
+ *           (DEVICE arrays of G pointers into every rank's receive buffer, offset to this rank's row
+ *           block) are given, straight into the peers' memory over NVLink (fused transpose);
+ *   stage2: y-transform of the received [nlv][nly][nx/G] complex128 into the real column slabs
+ *           conc_slab/flx_slab [nlv][ny][nx/G] float64 (device).
+ * Both stages are enqueued on the plan's stream; BLDFM_ASYNC skips the final synchronisation. */
+int  bldfm_sharded_stage1(bldfm_plan *plan, const bldfm_problem *prob, const int64_t *levels, int32_t nlv,
+                          int flags, int32_t rank, int32_t nranks, void *send_p, void *send_q,
+                          void *const *peer_p, void *const *peer_q);
+int  bldfm_sharded_stage2(bldfm_plan *plan, int32_t nlv, int flags, int32_t rank, int32_t nranks,
+                          const void *recv_p, const void *recv_q, void *conc_slab, void *flx_slab);
+/* CUDA IPC helpers for the fused transpose (device memory from bldfm_device_alloc only). */
+int  bldfm_ipc_export(void *dev_ptr, unsigned char *handle64);
+int  bldfm_ipc_open(int device, const unsigned char *handle64, void **out);
+int  bldfm_ipc_close(int device, void *p);
+
 /* Spectral-stage export for parity tests: the combined, phase-shifted spectra tfftp/tfftq
  * [nlv][nly][nlx] complex128 (host) as they stand before src/bldfm/solver.py:265. */
 int  bldfm_solve_spectral(bldfm_plan *plan, const bldfm_problem *prob, const int64_t *levels,

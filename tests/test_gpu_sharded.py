@@ -1,0 +1,84 @@
+"""ky-slab sharded solve: world_size 1 on any GPU box, world_size 2 (NCCL all-to-all and
+the fused peer-store transpose) when two GPUs are visible."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(n=96, nz=16):
+    from bldfm_b200.pbl_model import vertical_profiles
+    z, prof = vertical_profiles(nz, 10.0, (-3.0, -4.0), ustar=0.4, mol=-50.0)
+    return dict(srf_flx=np.zeros((n, n)), z=z, profiles=prof, domain=(n * 7.8125, n * 7.8125),
+                levels=[3, nz], modes=(n, n), meas_pt=(n * 3.9, n * 3.1), footprint=True, precision="double")
+
+
+def test_sharded_world1_equals_plain(gpu_lib):
+    import bldfm_b200
+    from bldfm_b200.sharded import steady_state_transport_solver_sharded
+    kw = _problem()
+    g0, c0, f0 = bldfm_b200.steady_state_transport_solver(**kw)
+    g1, c1, f1 = steady_state_transport_solver_sharded(**kw)
+    assert np.array_equal(c0, c1) and np.array_equal(f0, f1)
+    for a, b in zip(g0, g1):
+        assert np.array_equal(a, b)
+    with pytest.raises(NotImplementedError):
+        steady_state_transport_solver_sharded(**{**kw, "footprint": False})
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    sys.path.insert(0, str(ROOT))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import bldfm_b200
+        from bldfm_b200.sharded import release_peer_buffers, steady_state_transport_solver_sharded
+        bldfm_b200.config.DEVICE = rank
+        kw = _problem()
+        _, c0, f0 = bldfm_b200.steady_state_transport_solver(**kw)
+        res = {}
+        for fused in (False, True):
+            for rep in range(2):
+                _, c1, f1 = steady_state_transport_solver_sharded(fused=fused, **kw)
+            res[f"fused={fused}"] = bool(np.array_equal(c0, c1) and np.array_equal(f0, f1))
+            _, cs, fs = steady_state_transport_solver_sharded(fused=fused, gather=False, **kw)
+            nxl = c0.shape[-1] // world
+            res[f"slab fused={fused}"] = bool(np.array_equal(cs, c0[..., rank * nxl:(rank + 1) * nxl]))
+        release_peer_buffers()
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_world2_nccl_and_fused(gpu_lib):
+    if gpu_lib.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, res in out:
+        assert all(res.values()), (rank, res)
