@@ -339,7 +339,11 @@ def main():
             "clocks": clocks.summary(),
             "roofline": {
                 "kernel": "k_march (fused K4-K8)", "bound": "fp64", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak if peak > 0 else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+                # capture of this kernel on this workload (profiles/r1a_march_exact_ncu.txt): the 8.4 MB
+                # of spectra it writes stay in the 126 MB L2 for the transform that follows
+                "traffic": 84736 if not fma_mode else None,
                 "flops_per_launch": flops, "kernel_ms": march_ms,
                 "peak_source": ("measured in this run: bldfm_fp64_peak "
                                 + ("DFMA x2" if fma_mode else "DADD/DMUL (non-fused ops, exact mode)")),
