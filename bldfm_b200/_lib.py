@@ -34,6 +34,7 @@ SRC_ON_DEVICE = 0x010
 OUT_ON_DEVICE = 0x020
 ASYNC = 0x040
 FFT_LIBRARY = 0x080
+FFT_FULL = 0x100
 
 # every symbol include/bldfm_b200.h declares (tests check the library exports all of them)
 EXPORTS = [

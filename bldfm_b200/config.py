@@ -22,3 +22,5 @@ MARCH_MODE = os.environ.get("BLDFM_B200_MARCH", "exact")
 GRID_COPY = os.environ.get("BLDFM_B200_GRID_COPY", "0") == "1"
 # Force the library (cuFFT) transform path instead of the pruned in-house kernels.
 FFT_LIBRARY = os.environ.get("BLDFM_B200_FFT_LIBRARY", "0") == "1"
+# Use the full complex pruned passes instead of the real-output (Hermitian) half-work passes.
+FFT_FULL = os.environ.get("BLDFM_B200_FFT_FULL", "0") == "1"

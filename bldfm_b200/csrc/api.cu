@@ -20,6 +20,7 @@
 #include "march.cuh"
 #include "transform.cuh"
 #include "fft.cuh"
+#include "fft_herm.cuh"
 
 using namespace bldfm;
 
@@ -657,12 +658,22 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         int nl = 0;
         PrunedFftTables tab;
         TRY(ensure_twiddles(pl, spec_f32, &tab));
-        TRY(pl->fft_work.ensure(pruned_fft_work_bytes(g, spec_f32, nfields)));
-        cudaError_t fe = spec_f32
-            ? pruned_fft_launch<float>(pl->stream, pl->smem_optin, g, forward_dir, pl->spec_p.p, pl->spec_q.p,
-                                       nfields, pl->fft_work.p, d_conc, d_flx, tab, &nl)
-            : pruned_fft_launch<double>(pl->stream, pl->smem_optin, g, forward_dir, pl->spec_p.p, pl->spec_q.p,
-                                        nfields, pl->fft_work.p, d_conc, d_flx, tab, &nl);
+        cudaError_t fe;
+        if (flags & BLDFM_FFT_FULL) {
+            TRY(pl->fft_work.ensure(pruned_fft_work_bytes(g, spec_f32, nfields)));
+            fe = spec_f32
+                ? pruned_fft_launch<float>(pl->stream, pl->smem_optin, g, forward_dir, pl->spec_p.p, pl->spec_q.p,
+                                           nfields, pl->fft_work.p, d_conc, d_flx, tab, &nl)
+                : pruned_fft_launch<double>(pl->stream, pl->smem_optin, g, forward_dir, pl->spec_p.p, pl->spec_q.p,
+                                            nfields, pl->fft_work.p, d_conc, d_flx, tab, &nl);
+        } else {
+            TRY(pl->fft_work.ensure(herm_work_bytes(g, spec_f32, nfields)));
+            fe = spec_f32
+                ? herm_fft_launch<float>(pl->stream, pl->smem_optin, g, forward_dir, pl->spec_p.p, pl->spec_q.p,
+                                         nfields, pl->fft_work.p, d_conc, d_flx, tab, &nl)
+                : herm_fft_launch<double>(pl->stream, pl->smem_optin, g, forward_dir, pl->spec_p.p, pl->spec_q.p,
+                                          nfields, pl->fft_work.p, d_conc, d_flx, tab, &nl);
+        }
         if (fe != cudaSuccess) return fail(BLDFM_ERR_CUDA, std::string("pruned FFT launch: ") + cudaGetErrorString(fe));
         pl->launches += nl;
     }

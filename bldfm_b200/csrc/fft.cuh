@@ -62,7 +62,10 @@ struct FftPassArgs {
 // XOR swizzle of the 16-byte element index inside one transform: keeps every access pattern of the
 // DIT stages (stride-1 in j for L >= 8, stride-8 blocks for L = 1) free of shared-memory bank
 // conflicts; it permutes elements only within aligned groups of eight.
-__device__ __forceinline__ int fft_swz(int i) { return i ^ ((i >> 3) & 7); }
+__device__ __forceinline__ int fft_swz(int i)
+{
+    return i ^ (((i >> 3) ^ (i >> 6) ^ (i >> 9)) & 7);
+}
 
 template <typename T> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
@@ -347,9 +350,16 @@ inline int fft_env_int(const char* name, int dflt)
 }
 
 // transforms per CTA for the two passes given the shared-memory budget
-inline int fft_pick_cw(int N, bool f32, size_t smem_optin, int want)
+// `ntrans_total` (transforms of the whole launch) shrinks cw for small launches so that the grid
+// still covers every SM a few times -- a 512x512 single-level solve has only ~500 transforms per pass.
+inline int fft_pick_cw(int N, bool f32, size_t smem_optin, int want, int64_t ntrans_total = -1, int num_sms = 148)
 {
-    int cw = fft_env_int("BLDFM_FFT_CW", want);
+    int cw = fft_env_int("BLDFM_FFT_CW", 0);
+    if (cw <= 0) {
+        cw = want;
+        if (ntrans_total > 0)
+            while (cw > 1 && ntrans_total / cw < (int64_t)3 * num_sms) cw /= 2;
+    }
     while (cw > 1 && fft_smem_bytes(N, cw, f32) > smem_optin / 2) cw /= 2;   // keep >= 2 CTAs / SM
     return cw;
 }

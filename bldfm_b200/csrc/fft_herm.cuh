@@ -1,0 +1,315 @@
+// fft_herm.cuh -- real-output back-transform on half the work (K9 + K10 + K11 fused).
+//
+// The fields the solver returns are the REAL part of a 2-D transform of the retained spectrum S
+// (src/bldfm/solver.py:282-287).  Re F[S] = F[H] with H = (S + S~)/2, S~[fy][fx] = conj(S[-fy][-fx]),
+// and F[H] is exactly real because H is Hermitian.  That symmetry halves both passes:
+//
+//   pass X  rows fy = 0 .. nly/2 only (A[-fy][x] = conj(A[fy][x]) is implied); the Hermitian combine
+//           of the two source rows happens in the load of the first butterfly stage;
+//   pass Y  two columns per complex transform: c[f] = A1[f] + i*A2[f] for f >= 0 and
+//           conj(A1[-f]) + i*conj(A2[-f]) for f < 0, so that F[c] = out1 + i*out2.
+//
+// Each transform is the same in-place shared-memory mixed-radix DIT FFT as fft.cuh, but the first
+// stage takes its operands straight from global memory (no zero-fill / scatter pass) and the last
+// stage stores the output window straight from registers (no final shared-memory round trip).
+#pragma once
+
+#include "fft.cuh"
+
+namespace bldfm {
+
+struct FftHArgs {
+    int32_t N, nstages;
+    int32_t radix[kFftMaxStages];
+    int32_t lshift[kFftMaxStages];
+    int32_t cw;                // transforms per CTA (rows in pass X, column pairs in pass Y)
+    int32_t ntrans;            // transforms per field
+    int32_t conj_io;           // 1: inverse transform through conj(FFT(conj(x)))
+    int32_t nlx, nly;          // retained modes of S
+    int32_t nrow;              // rows of A = nly/2 + 1
+    int32_t nx;                // kept columns
+    int32_t out_off, n_out;    // output window of this pass
+    int32_t nfields_first;
+    const void* in;            // pass X: S [field][nly][nlx]      pass Y: A [field][nrow][nx]
+    const void* in2;
+    void* out;                 // pass X: A [field][nrow][nx]      pass Y: real [field][ny][nx]
+    void* out2;
+    const void* twiddle;
+    const int32_t* rev;
+};
+
+// S[fy][fx] with zero outside the retained set (signed frequencies)
+template <typename T>
+__device__ __forceinline__ Cplx<T> herm_s(const typename Vec2<T>::type* __restrict__ S, int nlx, int nly, int fy, int fx)
+{
+    if (fy < -(nly / 2) || fy > (nly - 1) / 2 || fx < -(nlx / 2) || fx > (nlx - 1) / 2) return {(T)0, (T)0};
+    const int ky = fy >= 0 ? fy : fy + nly;
+    const int kx = fx >= 0 ? fx : fx + nlx;
+    const typename Vec2<T>::type v = S[(size_t)ky * nlx + kx];
+    return {v.x, v.y};
+}
+
+// pass X operand: sum over the signed frequencies f == i (mod N), |f| <= nlx/2, of H[fy][f]
+template <typename T>
+__device__ __forceinline__ Cplx<T> herm_load_x(const FftHArgs& a, const typename Vec2<T>::type* __restrict__ S, int fy, int i)
+{
+    const int hmax = a.nlx / 2;
+    Cplx<T> acc = {(T)0, (T)0};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int f = k == 0 ? i : i - a.N;     // the signed frequencies congruent to i
+        if (f > hmax || f < -hmax) continue;
+        const Cplx<T> s1 = herm_s<T>(S, a.nlx, a.nly, fy, f);
+        const Cplx<T> s2 = herm_s<T>(S, a.nlx, a.nly, -fy, -f);
+        acc.r += (T)0.5 * (s1.r + s2.r);
+        acc.i += (T)0.5 * (s1.i - s2.i);
+    }
+    return acc;
+}
+
+// pass Y operand for the column pair (x1, x1+1)
+template <typename T>
+__device__ __forceinline__ Cplx<T> herm_load_y(const FftHArgs& a, const typename Vec2<T>::type* __restrict__ A, int x1, int i)
+{
+    const int hmax = a.nly / 2;
+    Cplx<T> acc = {(T)0, (T)0};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int f = k == 0 ? i : i - a.N;
+        if (f > hmax || f < -hmax) continue;
+        const int af = f >= 0 ? f : -f;
+        const typename Vec2<T>::type v1 = A[(size_t)af * a.nx + x1];
+        typename Vec2<T>::type v2 = mk2<T>((T)0, (T)0);
+        if (x1 + 1 < a.nx) v2 = A[(size_t)af * a.nx + x1 + 1];
+        if (f == 0) { acc.r += v1.x; acc.i += v2.x; }                    // A[0] is real
+        else if (f > 0) { acc.r += v1.x - v2.y; acc.i += v1.y + v2.x; }  // A1 + i*A2
+        else { acc.r += v1.x + v2.y; acc.i += v2.x - v1.y; }             // conj(A1) + i*conj(A2)
+    }
+    return acc;
+}
+
+template <typename T, int PASS>
+__device__ __forceinline__ void herm_emit(const FftHArgs& a, void* outp, size_t field, int tg, int i, Cplx<T> v, T sgn)
+{
+    using V = typename Vec2<T>::type;
+    const int o = i - a.out_off;
+    if (o < 0 || o >= a.n_out) return;
+    if (PASS == 0) {
+        reinterpret_cast<V*>(outp)[(field * a.nrow + tg) * (size_t)a.nx + o] = mk2<T>(v.r, sgn * v.i);
+    } else {
+        T* dst = reinterpret_cast<T*>(outp) + (field * a.n_out + o) * (size_t)a.nx + 2 * tg;
+        const T im = sgn * v.i;
+        if (2 * tg + 1 < a.nx) {
+            if ((reinterpret_cast<uintptr_t>(dst) & (sizeof(V) - 1)) == 0) *reinterpret_cast<V*>(dst) = mk2<T>(v.r, im);
+            else { dst[0] = v.r; dst[1] = im; }
+        } else {
+            dst[0] = v.r;
+        }
+    }
+}
+
+template <typename T, int PASS, int R>
+__device__ __forceinline__ void herm_first_stage(const FftHArgs& a, typename Vec2<T>::type* buf,
+                                                 const typename Vec2<T>::type* __restrict__ src, void* outp,
+                                                 size_t field, int t0, int cw, T sgn)
+{
+    const int N = a.N;
+    const int nb = N / R;
+    const int total = nb * cw;
+    for (int b = threadIdx.x; b < total; b += (int)blockDim.x) {
+        int t, il;
+        if (PASS == 1) { il = b / cw; t = b - il * cw; }     // lanes walk the column pairs first
+        else { t = b / nb; il = b - t * nb; }                // lanes walk the frequency index
+        Cplx<T> v[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+            const int i = il + u * nb;
+            v[u] = PASS == 0 ? herm_load_x<T>(a, src, t0 + t, i) : herm_load_y<T>(a, src, 2 * (t0 + t), i);
+            v[u].i *= sgn;
+        }
+        if (R == 2) bfly2<T>(v);
+        else if (R == 3) bfly3<T>(v);
+        else if (R == 4) bfly4<T>(v);
+        else if (R == 5) bfly5<T>(v);
+        else bfly8<T>(v);
+        if (a.nstages == 1) {
+#pragma unroll
+            for (int q = 0; q < R; ++q) herm_emit<T, PASS>(a, outp, field, t0 + t, q, v[q], sgn);
+        } else {
+            const int base = a.rev[il];
+            typename Vec2<T>::type* p = buf + (size_t)t * (N + kFftPad);
+#pragma unroll
+            for (int q = 0; q < R; ++q) p[fft_swz(base + q)] = mk2<T>(v[q].r, v[q].i);
+        }
+    }
+}
+
+template <typename T, int PASS, int R>
+__device__ __forceinline__ void herm_last_stage(const FftHArgs& a, const typename Vec2<T>::type* buf,
+                                                const typename Vec2<T>::type* __restrict__ tw, void* outp,
+                                                size_t field, int t0, int cw, T sgn)
+{
+    using V = typename Vec2<T>::type;
+    const int N = a.N;
+    const int L = N / R;
+    const int total = L * cw;
+    for (int b = threadIdx.x; b < total; b += (int)blockDim.x) {
+        int t, j;
+        if (PASS == 1) { j = b / cw; t = b - j * cw; }
+        else { t = b / L; j = b - t * L; }
+        // skip butterflies none of whose outputs lie in the window
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < R; ++q) { const int o = j + q * L - a.out_off; any |= (o >= 0 && o < a.n_out); }
+        if (!any) continue;
+        const V* p = buf + (size_t)t * (N + kFftPad);
+        Cplx<T> v[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u) { const V x = p[fft_swz(j + u * L)]; v[u] = {x.x, x.y}; }
+        {
+            const V w1v = tw[j];
+            const Cplx<T> w1 = {w1v.x, w1v.y};
+            if (R == 2) {
+                v[1] = cmul<T>(v[1], w1);
+            } else if (R == 3) {
+                const Cplx<T> w2 = cmul<T>(w1, w1);
+                v[1] = cmul<T>(v[1], w1); v[2] = cmul<T>(v[2], w2);
+            } else if (R == 4) {
+                const Cplx<T> w2 = cmul<T>(w1, w1), w3 = cmul<T>(w2, w1);
+                v[1] = cmul<T>(v[1], w1); v[2] = cmul<T>(v[2], w2); v[3] = cmul<T>(v[3], w3);
+            } else if (R == 5) {
+                const Cplx<T> w2 = cmul<T>(w1, w1), w3 = cmul<T>(w2, w1), w4 = cmul<T>(w2, w2);
+                v[1] = cmul<T>(v[1], w1); v[2] = cmul<T>(v[2], w2); v[3] = cmul<T>(v[3], w3);
+                v[4] = cmul<T>(v[4], w4);
+            } else {
+                const Cplx<T> w2 = cmul<T>(w1, w1), w3 = cmul<T>(w2, w1), w4 = cmul<T>(w2, w2);
+                const Cplx<T> w5 = cmul<T>(w4, w1), w6 = cmul<T>(w4, w2), w7 = cmul<T>(w4, w3);
+                v[1] = cmul<T>(v[1], w1); v[2] = cmul<T>(v[2], w2); v[3] = cmul<T>(v[3], w3);
+                v[4] = cmul<T>(v[4], w4); v[5] = cmul<T>(v[5], w5); v[6] = cmul<T>(v[6], w6);
+                v[7] = cmul<T>(v[7], w7);
+            }
+        }
+        if (R == 2) bfly2<T>(v);
+        else if (R == 3) bfly3<T>(v);
+        else if (R == 4) bfly4<T>(v);
+        else if (R == 5) bfly5<T>(v);
+        else bfly8<T>(v);
+#pragma unroll
+        for (int q = 0; q < R; ++q) herm_emit<T, PASS>(a, outp, field, t0 + t, j + q * L, v[q], sgn);
+    }
+}
+
+// grid = (ceil(ntrans/cw), fields) ; dynamic smem = cw*(N+pad)*sizeof(complex)
+template <typename T, int PASS>
+__global__ void __launch_bounds__(kFftMaxThreads, 2)
+k_fft_h(const FftHArgs a)
+{
+    using V = typename Vec2<T>::type;
+    extern __shared__ __align__(16) unsigned char fft_smem[];
+    V* buf = reinterpret_cast<V*>(fft_smem);
+    const int N = a.N;
+    const int t0 = blockIdx.x * a.cw;
+    const int cw = min(a.cw, a.ntrans - t0);
+    const bool second = (int)blockIdx.y >= a.nfields_first;
+    const size_t field = second ? blockIdx.y - a.nfields_first : blockIdx.y;
+    const size_t in_stride = PASS == 0 ? (size_t)a.nly * a.nlx : (size_t)a.nrow * a.nx;
+    const V* src = reinterpret_cast<const V*>(second ? a.in2 : a.in) + field * in_stride;
+    void* outp = second ? a.out2 : a.out;
+    const T sgn = a.conj_io ? (T)-1 : (T)1;
+    const V* tw = reinterpret_cast<const V*>(a.twiddle);
+
+    switch (a.radix[0]) {
+        case 2: herm_first_stage<T, PASS, 2>(a, buf, src, outp, field, t0, cw, sgn); break;
+        case 3: herm_first_stage<T, PASS, 3>(a, buf, src, outp, field, t0, cw, sgn); break;
+        case 4: herm_first_stage<T, PASS, 4>(a, buf, src, outp, field, t0, cw, sgn); break;
+        case 5: herm_first_stage<T, PASS, 5>(a, buf, src, outp, field, t0, cw, sgn); break;
+        default: herm_first_stage<T, PASS, 8>(a, buf, src, outp, field, t0, cw, sgn); break;
+    }
+    if (a.nstages == 1) return;
+    __syncthreads();
+    int L = a.radix[0];
+    for (int s = 1; s < a.nstages - 1; ++s) {
+        const int r = a.radix[s];
+        switch (r) {
+            case 2: fft_stage<T, 2>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
+            case 3: fft_stage<T, 3>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
+            case 4: fft_stage<T, 4>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
+            case 5: fft_stage<T, 5>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
+            default: fft_stage<T, 8>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
+        }
+        L *= r;
+        __syncthreads();
+    }
+    switch (a.radix[a.nstages - 1]) {
+        case 2: herm_last_stage<T, PASS, 2>(a, buf, tw, outp, field, t0, cw, sgn); break;
+        case 3: herm_last_stage<T, PASS, 3>(a, buf, tw, outp, field, t0, cw, sgn); break;
+        case 4: herm_last_stage<T, PASS, 4>(a, buf, tw, outp, field, t0, cw, sgn); break;
+        case 5: herm_last_stage<T, PASS, 5>(a, buf, tw, outp, field, t0, cw, sgn); break;
+        default: herm_last_stage<T, PASS, 8>(a, buf, tw, outp, field, t0, cw, sgn); break;
+    }
+}
+
+inline size_t herm_work_bytes(const bldfm_geometry& g, bool f32, int64_t nfields)
+{
+    const int64_t chunk = std::min<int64_t>(nfields, 16384);
+    return (size_t)2 * (size_t)chunk * (size_t)(g.nly / 2 + 1) * (size_t)g.nx * (f32 ? sizeof(float2) : sizeof(double2));
+}
+
+// both passes for the nfields spectra of spec_p (-> out_p) and spec_q (-> out_q): two launches
+template <typename T>
+inline cudaError_t herm_fft_launch(cudaStream_t stream, size_t smem_optin, const bldfm_geometry& g,
+                                   bool forward_dir, const void* spec_p, const void* spec_q, int64_t nfields,
+                                   void* work, void* out_p, void* out_q, const PrunedFftTables& tab, int* nlaunch)
+{
+    using V = typename Vec2<T>::type;
+    const bool f32 = sizeof(T) == 4;
+    std::vector<int> rx, ry;
+    fft_factorize(g.nfx, rx);
+    fft_factorize(g.nfy, ry);
+    const int nrow = g.nly / 2 + 1;
+
+    FftHArgs ax{};
+    ax.N = g.nfx; ax.nstages = (int)rx.size();
+    { FftPassArgs tmp{}; fft_set_stages(tmp, rx); for (int i = 0; i < tmp.nstages; ++i) { ax.radix[i] = tmp.radix[i]; ax.lshift[i] = tmp.lshift[i]; } }
+    ax.cw = fft_pick_cw(g.nfx, f32, smem_optin, 4, (int64_t)nrow * 2 * nfields);
+    ax.ntrans = nrow; ax.conj_io = forward_dir ? 0 : 1;
+    ax.nlx = g.nlx; ax.nly = g.nly; ax.nrow = nrow; ax.nx = g.nx;
+    ax.out_off = g.px; ax.n_out = g.nx;
+    ax.twiddle = tab.tw_x; ax.rev = tab.rev_x;
+
+    FftHArgs ay = ax;
+    ay.N = g.nfy; ay.nstages = (int)ry.size();
+    { FftPassArgs tmp{}; fft_set_stages(tmp, ry); for (int i = 0; i < tmp.nstages; ++i) { ay.radix[i] = tmp.radix[i]; ay.lshift[i] = tmp.lshift[i]; } }
+    ay.cw = fft_pick_cw(g.nfy, f32, smem_optin, 4, (int64_t)((g.nx + 1) / 2) * 2 * nfields);
+    ay.ntrans = (g.nx + 1) / 2;
+    ay.out_off = g.py; ay.n_out = g.ny;
+    ay.twiddle = tab.tw_y; ay.rev = tab.rev_y;
+
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_fft_h<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fft_h<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    if (e != cudaSuccess) return e;
+    const size_t sx = fft_smem_bytes(ax.N, ax.cw, f32), sy = fft_smem_bytes(ay.N, ay.cw, f32);
+    const int64_t chunk = 16384;
+    for (int64_t f0 = 0; f0 < nfields; f0 += chunk) {
+        const int nf = (int)std::min<int64_t>(chunk, nfields - f0);
+        FftHArgs bx = ax, by = ay;
+        bx.nfields_first = nf; by.nfields_first = nf;
+        bx.in = reinterpret_cast<const V*>(spec_p) + (size_t)f0 * g.nly * g.nlx;
+        bx.in2 = reinterpret_cast<const V*>(spec_q) + (size_t)f0 * g.nly * g.nlx;
+        bx.out = work;
+        bx.out2 = reinterpret_cast<V*>(work) + (size_t)nf * nrow * g.nx;
+        by.in = bx.out; by.in2 = bx.out2;
+        by.out = reinterpret_cast<T*>(out_p) + (size_t)f0 * g.ny * g.nx;
+        by.out2 = reinterpret_cast<T*>(out_q) + (size_t)f0 * g.ny * g.nx;
+        k_fft_h<T, 0><<<dim3((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), (unsigned)(2 * nf)),
+                        fft_pick_threads(ax.N, ax.cw, ax.radix[0]), sx, stream>>>(bx);
+        k_fft_h<T, 1><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), (unsigned)(2 * nf)),
+                        fft_pick_threads(ay.N, ay.cw, ay.radix[0]), sy, stream>>>(by);
+        *nlaunch += 2;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace bldfm

@@ -37,6 +37,8 @@ def _flags(footprint, analytic, precision):
         raise ValueError("bldfm_b200.config.MARCH_MODE must be 'exact' or 'fma'")
     if config.FFT_LIBRARY:
         f |= _lib.FFT_LIBRARY
+    if config.FFT_FULL:
+        f |= _lib.FFT_FULL
     return f
 
 

@@ -44,6 +44,7 @@ extern "C" {
 #define BLDFM_OUT_ON_DEVICE    0x020  /* conc/flx are device pointers                                             */
 #define BLDFM_ASYNC            0x040  /* with BLDFM_OUT_ON_DEVICE: enqueue on the plan's stream, do not sync      */
 #define BLDFM_FFT_LIBRARY      0x080  /* force the cuFFT transform path instead of the pruned in-house kernels    */
+#define BLDFM_FFT_FULL         0x100  /* in-house back-transform without the real-output (Hermitian) halving      */
 
 typedef struct bldfm_plan bldfm_plan;
 

@@ -81,6 +81,7 @@ def main():
     if args.check:
         _, c, f = run(False, True)
         if rank == 0:
+            bldfm_b200.config.FFT_FULL = True
             _, c0, f0 = bldfm_b200.steady_state_transport_solver(**kw)
             out["equal_to_unsharded"] = bool(np.array_equal(c0, np.squeeze(c.cpu().numpy())) and
                                              np.array_equal(f0, np.squeeze(f.cpu().numpy())))

@@ -32,10 +32,11 @@ for name, kw in (("cfg2", config2()), ("cfg3_512x65", config3(512, 64))):
 print(json.dumps(out))
 ''' % str(ROOT)
 
-settings = [("default", {})]
-for cw in (1, 2, 4):
-    for th in (128, 192, 256, 384):
-        settings.append((f"cw{cw}_t{th}", {"BLDFM_FFT_CW": str(cw), "BLDFM_FFT_THREADS": str(th)}))
+settings = [("default", {}), ("full", {"BLDFM_B200_FFT_FULL": "1"}), ("library", {"BLDFM_B200_FFT_LIBRARY": "1"})]
+if "--sweep" in sys.argv:
+    for cw in (1, 2, 4):
+        for th in (128, 192, 256, 384):
+            settings.append((f"cw{cw}_t{th}", {"BLDFM_FFT_CW": str(cw), "BLDFM_FFT_THREADS": str(th)}))
 for name, env in settings:
     e = dict(os.environ, **env)
     r = subprocess.run([sys.executable, "-c", CHILD], env=e, capture_output=True, text=True, cwd=str(ROOT))

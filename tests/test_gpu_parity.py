@@ -77,16 +77,20 @@ def test_spectral_stage_against_oracle(B, oracle, name, precision):
     assert rel_l2c(tq, otq) <= tol, rel_l2c(tq, otq)
 
 
-@pytest.mark.parametrize("library_fft", [False, True])
+@pytest.mark.parametrize("fft", ["hermitian", "full", "library"])
 @pytest.mark.parametrize("name", SOLVE_CASES)
 @pytest.mark.parametrize("precision", ["single", "double"])
-def test_solve_against_reference_golden(B, name, precision, library_fft):
+def test_solve_against_reference_golden(B, name, precision, fft):
+    """All three back-transform paths: real-output half-work passes (default), full complex pruned
+    passes, and the cuFFT library path."""
     kw, d = load_case(name)
-    B.config.FFT_LIBRARY = library_fft
+    B.config.FFT_LIBRARY = fft == "library"
+    B.config.FFT_FULL = fft == "full"
     try:
         grid, conc, flx = B.steady_state_transport_solver(precision=precision, **kw)
     finally:
         B.config.FFT_LIBRARY = False
+        B.config.FFT_FULL = False
     ref_c, ref_f = d[f"conc_{precision}"], d[f"flx_{precision}"]
     assert conc.shape == ref_c.shape and flx.shape == ref_f.shape
     assert conc.dtype == ref_c.dtype and flx.dtype == ref_f.dtype

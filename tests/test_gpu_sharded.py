@@ -23,9 +23,18 @@ def test_sharded_world1_equals_plain(gpu_lib):
     import bldfm_b200
     from bldfm_b200.sharded import steady_state_transport_solver_sharded
     kw = _problem()
-    g0, c0, f0 = bldfm_b200.steady_state_transport_solver(**kw)
+    # the sharded passes are the full complex ones: bitwise equal to the plain solver in that mode,
+    # and equal to round-off to the default real-output (Hermitian) passes
+    bldfm_b200.config.FFT_FULL = True
+    try:
+        g0, c0, f0 = bldfm_b200.steady_state_transport_solver(**kw)
+    finally:
+        bldfm_b200.config.FFT_FULL = False
     g1, c1, f1 = steady_state_transport_solver_sharded(**kw)
     assert np.array_equal(c0, c1) and np.array_equal(f0, f1)
+    _, c2, f2 = bldfm_b200.steady_state_transport_solver(**kw)
+    assert np.abs(c2 - c1).max() <= 1e-13 * np.abs(c1).max()
+    assert np.abs(f2 - f1).max() <= 1e-13 * np.abs(f1).max()
     for a, b in zip(g0, g1):
         assert np.array_equal(a, b)
     with pytest.raises(NotImplementedError):
@@ -51,7 +60,9 @@ def _worker(rank, world, port, q):
         from bldfm_b200.sharded import release_peer_buffers, steady_state_transport_solver_sharded
         bldfm_b200.config.DEVICE = rank
         kw = _problem()
+        bldfm_b200.config.FFT_FULL = True
         _, c0, f0 = bldfm_b200.steady_state_transport_solver(**kw)
+        bldfm_b200.config.FFT_FULL = False
         res = {}
         for fused in (False, True):
             for rep in range(2):
