@@ -29,6 +29,10 @@ constexpr int kFftMaxStages = 12;
 constexpr int kFftMaxThreads = 384;
 constexpr int kFftPad = 2;   // elements of padding between the transforms of one CTA
 
+// shared-memory elements reserved per transform: the XOR swizzle permutes within aligned groups of
+// eight, so the last group must exist in full even when N is not a multiple of 8
+__host__ __device__ __forceinline__ int fft_stride(int N) { return ((N + 7) & ~7) + kFftPad; }
+
 struct FftPassArgs {
     int32_t N;                 // transform length
     int32_t nstages;
@@ -166,7 +170,7 @@ __device__ __forceinline__ void fft_stage(typename Vec2<T>::type* buf, const typ
         int blk, j;
         if (lshift >= 0) { blk = jj >> lshift; j = jj & (L - 1); }
         else { blk = (int)((unsigned)jj / (unsigned)L); j = jj - blk * L; }
-        V* p = buf + (size_t)t * (N + kFftPad);
+        V* p = buf + (size_t)t * fft_stride(N);
         const int i0 = blk * L * R + j;
         Cplx<T> v[R];
 #pragma unroll
@@ -229,7 +233,7 @@ k_fft_pass(const FftPassArgs a)
     const T sgn = a.conj_io ? (T)-1 : (T)1;
 
     // zero fill, then scatter the non-zero inputs to their digit-reversed slots
-    for (int e = threadIdx.x; e < cw * (N + kFftPad); e += (int)blockDim.x) buf[e] = mk2<T>((T)0, (T)0);
+    for (int e = threadIdx.x; e < cw * fft_stride(N); e += (int)blockDim.x) buf[e] = mk2<T>((T)0, (T)0);
     __syncthreads();
     const int npos_in = (a.n_in + 1) / 2;
     for (int e = threadIdx.x; e < cw * a.n_in; e += (int)blockDim.x) {
@@ -241,7 +245,7 @@ k_fft_pass(const FftPassArgs a)
         T xr, xi;
         if (REAL_IN) { xr = reinterpret_cast<const T*>(inp)[g]; xi = (T)0; }
         else { const V x = reinterpret_cast<const V*>(inp)[g]; xr = x.x; xi = x.y; }
-        buf[(size_t)t * (N + kFftPad) + fft_swz(a.rev[i])] = mk2<T>(xr, sgn * xi);
+        buf[(size_t)t * fft_stride(N) + fft_swz(a.rev[i])] = mk2<T>(xr, sgn * xi);
     }
     __syncthreads();
 
@@ -270,7 +274,7 @@ k_fft_pass(const FftPassArgs a)
         if (a.t_fast) { j = e / cw; t = e - j * cw; }
         else          { t = e / a.n_out; j = e - t * a.n_out; }
         const int i = a.out_freq ? (j < npos_out ? j : j - a.n_out + N) : a.out_off + j;
-        const V x = buf[(size_t)t * (N + kFftPad) + fft_swz(i)];
+        const V x = buf[(size_t)t * fft_stride(N) + fft_swz(i)];
         size_t o = field * a.out_field_stride + (size_t)(t0 + t) * a.out_tstride;
         void* dst = outp;
         if (a.out_block > 0) {
@@ -340,7 +344,7 @@ inline void fft_rev_table(int N, const std::vector<int>& radix, std::vector<int3
 
 inline size_t fft_smem_bytes(int N, int cw, bool f32)
 {
-    return (size_t)cw * (size_t)(N + kFftPad) * (f32 ? sizeof(float2) : sizeof(double2));
+    return (size_t)cw * (size_t)fft_stride(N) * (f32 ? sizeof(float2) : sizeof(double2));
 }
 
 inline int fft_env_int(const char* name, int dflt)

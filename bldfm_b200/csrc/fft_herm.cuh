@@ -137,7 +137,7 @@ __device__ __forceinline__ void herm_first_stage(const FftHArgs& a, typename Vec
             for (int q = 0; q < R; ++q) herm_emit<T, PASS>(a, outp, field, t0 + t, q, v[q], sgn);
         } else {
             const int base = a.rev[il];
-            typename Vec2<T>::type* p = buf + (size_t)t * (N + kFftPad);
+            typename Vec2<T>::type* p = buf + (size_t)t * fft_stride(N);
 #pragma unroll
             for (int q = 0; q < R; ++q) p[fft_swz(base + q)] = mk2<T>(v[q].r, v[q].i);
         }
@@ -162,7 +162,7 @@ __device__ __forceinline__ void herm_last_stage(const FftHArgs& a, const typenam
 #pragma unroll
         for (int q = 0; q < R; ++q) { const int o = j + q * L - a.out_off; any |= (o >= 0 && o < a.n_out); }
         if (!any) continue;
-        const V* p = buf + (size_t)t * (N + kFftPad);
+        const V* p = buf + (size_t)t * fft_stride(N);
         Cplx<T> v[R];
 #pragma unroll
         for (int u = 0; u < R; ++u) { const V x = p[fft_swz(j + u * L)]; v[u] = {x.x, x.y}; }

@@ -220,3 +220,36 @@ def test_cache_roundtrip(B, tmp_path):
     assert np.array_equal(r1[1], r2[1]) and np.array_equal(r1[2], r2[2])
     for a, b in zip(r1[0], r2[0]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("fft", ["hermitian", "full", "library"])
+@pytest.mark.parametrize("shape,modes,halo", [
+    ((32, 48), (48, 32), 0.0),        # no halo: transform length == retained modes (Nyquist aliases)
+    ((30, 20), (20, 30), 0.0),        # sizes with factors 3 and 5
+    ((24, 40), (16, 8), 35.0),        # truncated modes, small halo
+    ((2, 2), (2, 2), None),           # smallest grid
+    ((15, 45), (512, 512), 0.0),      # odd sizes 3^2*5 x 3*5, modes clamped to odd counts, in-house path
+    ((33, 21), (512, 512), 50.0),     # odd sizes, modes clamped; 7 and 11 as factors -> library fallback
+])
+def test_edge_geometries_against_oracle(B, oracle, shape, modes, halo, fft):
+    from bldfm_b200.pbl_model import vertical_profiles
+    from bldfm_b200.utils import ideal_source
+    ny, nx = shape
+    dom = (nx * 9.0, ny * 11.0)
+    z, prof = vertical_profiles(12, 8.0, (2.5, -3.5), ustar=0.35, mol=-80.0)
+    rng = np.random.default_rng(nx * 100 + ny)
+    src = rng.random((ny, nx))
+    B.config.FFT_LIBRARY = fft == "library"
+    B.config.FFT_FULL = fft == "full"
+    try:
+        for footprint in (True, False):
+            kw = dict(srf_flx=src, z=z, profiles=prof, domain=dom, levels=[0, 7, 12], modes=modes,
+                      meas_pt=(dom[0] * 0.4, dom[1] * 0.6), footprint=footprint, halo=halo, precision="double")
+            _, c, f = B.steady_state_transport_solver(**kw)
+            _, oc, of = oracle.solve(**kw)
+            assert c.shape == oc.shape
+            assert rel_l2(c, oc) <= TOL_F64, (footprint, rel_l2(c, oc))
+            assert rel_l2(f, of) <= TOL_F64, (footprint, rel_l2(f, of))
+    finally:
+        B.config.FFT_LIBRARY = False
+        B.config.FFT_FULL = False
