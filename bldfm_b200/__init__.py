@@ -6,7 +6,7 @@ C ABI of include/bldfm_b200.h.  No CPU fallback: without the built library and a
 compute calls raise.
 """
 
-from .solver import steady_state_transport_solver, ivp_solver, solve_batched  # noqa: F401
+from .solver import steady_state_transport_solver, ivp_solver, solve_batched, measure_batched  # noqa: F401
 from .utils import compute_wind_fields, ideal_source, point_measurement  # noqa: F401
 from .interface import (  # noqa: F401
     run_bldfm_single,
@@ -22,6 +22,7 @@ __all__ = [
     "steady_state_transport_solver",
     "ivp_solver",
     "solve_batched",
+    "measure_batched",
     "compute_wind_fields",
     "ideal_source",
     "point_measurement",

@@ -45,7 +45,7 @@ EXPORTS = [
     "bldfm_solve", "bldfm_solve_batched", "bldfm_solve_spectral", "bldfm_march",
     "bldfm_host_alloc", "bldfm_host_free", "bldfm_device_alloc", "bldfm_device_free",
     "bldfm_memcpy_d2h", "bldfm_memcpy_h2d", "bldfm_fp64_peak",
-    "bldfm_sharded_stage1", "bldfm_sharded_stage2", "bldfm_ipc_export", "bldfm_ipc_open", "bldfm_ipc_close",
+    "bldfm_solve_batched_measure", "bldfm_sharded_stage1", "bldfm_sharded_stage2", "bldfm_ipc_export", "bldfm_ipc_open", "bldfm_ipc_close",
 ]
 
 
@@ -129,6 +129,7 @@ def lib():
         "bldfm_memcpy_d2h": (C.c_int, [C.c_int, vp, vp, i64]),
         "bldfm_memcpy_h2d": (C.c_int, [C.c_int, vp, vp, i64]),
         "bldfm_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, _DP]),
+        "bldfm_solve_batched_measure": (C.c_int, [vp, i32, PP, I64P, i32, vp, C.c_int, vp, vp, vp]),
         "bldfm_sharded_stage1": (C.c_int, [vp, PP, I64P, i32, C.c_int, i32, i32, vp, vp, vp, vp]),
         "bldfm_sharded_stage2": (C.c_int, [vp, i32, C.c_int, i32, i32, vp, vp, vp, vp]),
         "bldfm_ipc_export": (C.c_int, [vp, C.c_char_p]),

@@ -107,6 +107,7 @@ struct bldfm_plan {
     DevBuf fft_work;         // pruned path: intermediate [field][nly][nx]
     DevBuf tw64, tw32;       // pruned path: twiddle tables  x[nfx] | y[nfy]  (double2 / float2)
     DevBuf out_c, out_f;     // device outputs when the caller wants host results
+    DevBuf weight, partial;  // f-4 weighted sums: weight map [ny][nx], partial sums | results
     Staging staging[kStagingSlots];
     int staging_next = 0;
     std::map<uint64_t, cufftHandle> fft_plans;
@@ -833,6 +834,7 @@ int bldfm_plan_destroy(bldfm_plan* pl)
     for (auto& kv : pl->fft_plans) cufftDestroy(kv.second);
     pl->tables.release(); pl->params.release(); pl->spec_p.release(); pl->spec_q.release();
     pl->pad_in.release(); pl->pad_out.release(); pl->src_in.release(); pl->src_pad.release();
+    pl->weight.release(); pl->partial.release();
     pl->fft_work.release(); pl->tw64.release(); pl->tw32.release(); pl->out_c.release(); pl->out_f.release();
     for (auto& s : pl->staging) {
         if (s.host) cudaFreeHost(s.host);
@@ -902,6 +904,52 @@ int bldfm_solve_batched(bldfm_plan* plan, int32_t nprob, const bldfm_problem* pr
     if (!conc || !flx) return fail(BLDFM_ERR_INVALID, "output pointer is NULL");
     SolveOut o; o.conc = conc; o.flx = flx;
     return solve_impl(plan, nprob, probs, levels, nlv, srf_flx, flags, o);
+}
+
+int bldfm_solve_batched_measure(bldfm_plan* pl, int32_t nprob, const bldfm_problem* probs,
+                                const int64_t* levels, int32_t nlv, const double* srf_flx, int flags,
+                                const double* weight, double* conc_w, double* flx_w)
+{
+    if (!pl || !weight || !conc_w || !flx_w) return fail(BLDFM_ERR_INVALID, "NULL argument");
+    if (nprob < 1 || nlv < 1) return fail(BLDFM_ERR_INVALID, "bad sizes");
+    const bldfm_geometry& g = pl->g;
+    DeviceGuard guard(pl->device);
+    if (!guard.ok) return fail(BLDFM_ERR_CUDA, "cudaSetDevice failed");
+    const int64_t per_field = (int64_t)g.nx * g.ny;
+    const int64_t nfields = (int64_t)nprob * nlv;
+    // decide the field dtype the same way solve_impl does
+    bool any_shift = false, all_shift = true;
+    for (int b = 0; b < nprob; ++b) {
+        const bool sh = (flags & BLDFM_FOOTPRINT) || (probs[b].xm * probs[b].xm + probs[b].ym * probs[b].ym > 0.0);
+        any_shift |= sh; all_shift &= sh;
+    }
+    const bool f32 = !(flags & BLDFM_DOUBLE) && !any_shift;
+    const size_t relem = f32 ? sizeof(float) : sizeof(double);
+    TRY(pl->out_c.ensure((size_t)nfields * per_field * relem));
+    TRY(pl->out_f.ensure((size_t)nfields * per_field * relem));
+    TRY(pl->weight.ensure((size_t)per_field * sizeof(double)));
+    TRY(pl->partial.ensure((size_t)2 * nfields * (kReduceBlocks + 1) * sizeof(double)));
+    CUDA_TRY(cudaMemcpyAsync(pl->weight.p, weight, (size_t)per_field * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+    SolveOut o; o.conc = pl->out_c.p; o.flx = pl->out_f.p;
+    if (nfields > 32767) return fail(BLDFM_ERR_INVALID, "too many fields in one measurement batch (max 32767)");
+    const int f2 = flags | BLDFM_OUT_ON_DEVICE | BLDFM_ASYNC;
+    TRY(solve_impl(pl, nprob, probs, levels, nlv, srf_flx, f2, o));
+    double* partial = static_cast<double*>(pl->partial.p);
+    double* result = partial + (size_t)2 * nfields * kReduceBlocks;
+    for (int which = 0; which < 2; ++which) {
+        const void* src = which == 0 ? pl->out_c.p : pl->out_f.p;
+        double* part = partial + (size_t)which * nfields * kReduceBlocks;
+        const dim3 grid(kReduceBlocks, (unsigned)nfields);
+        if (f32) k_weighted_partial<float><<<grid, 256, 0, pl->stream>>>(static_cast<const float*>(src), static_cast<const double*>(pl->weight.p), part, per_field);
+        else k_weighted_partial<double><<<grid, 256, 0, pl->stream>>>(static_cast<const double*>(src), static_cast<const double*>(pl->weight.p), part, per_field);
+    }
+    k_weighted_final<<<(unsigned)((2 * nfields + 127) / 128), 128, 0, pl->stream>>>(partial, result, (int)(2 * nfields), kReduceBlocks);
+    CUDA_TRY(cudaGetLastError());
+    pl->launches += 3;
+    CUDA_TRY(cudaMemcpyAsync(conc_w, result, (size_t)nfields * sizeof(double), cudaMemcpyDeviceToHost, pl->stream));
+    CUDA_TRY(cudaMemcpyAsync(flx_w, result + nfields, (size_t)nfields * sizeof(double), cudaMemcpyDeviceToHost, pl->stream));
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return BLDFM_OK;
 }
 
 int bldfm_solve_spectral(bldfm_plan* plan, const bldfm_problem* prob, const int64_t* levels,

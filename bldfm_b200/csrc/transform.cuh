@@ -69,4 +69,40 @@ k_crop_real(const C* __restrict__ src, R* __restrict__ dst, int nx, int ny, int 
     }
 }
 
+// f-4: footprint-weighted sums sum_{y,x} field[f][y][x] * w[y][x]  (point_measurement, utils.py:80-92)
+// stage 1: kReduceBlocks partial sums per field (fixed assignment -> deterministic order)
+constexpr int kReduceBlocks = 64;
+
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_weighted_partial(const R* __restrict__ fields, const double* __restrict__ w, double* __restrict__ partial,
+                   int64_t per_field)
+{
+    const int f = blockIdx.y;
+    const R* src = fields + (size_t)f * per_field;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_field;
+         i += (int64_t)gridDim.x * blockDim.x)
+        acc = fma((double)src[i], w[i], acc);
+    __shared__ double red[256];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(size_t)f * gridDim.x + blockIdx.x] = red[0];
+}
+
+// stage 2: one thread per field adds its partial sums in index order
+__global__ void __launch_bounds__(128)
+k_weighted_final(const double* __restrict__ partial, double* __restrict__ out, int nfields, int nblocks)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfields) return;
+    double acc = 0.0;
+    for (int b = 0; b < nblocks; ++b) acc += partial[(size_t)f * nblocks + b];
+    out[f] = acc;
+}
+
 }  // namespace bldfm

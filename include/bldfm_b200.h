@@ -134,6 +134,15 @@ int  bldfm_solve_batched(bldfm_plan *plan, int32_t nprob, const bldfm_problem *p
                          const int64_t *levels, int32_t nlv, const double *srf_flx, int flags,
                          void *conc, void *flx);
 
+/* Footprint-weighted measurements without moving the fields to the host: for every problem b and
+ * level row r returns sum_{y,x} conc[b][r][y][x]*weight[y][x] and the same for flx -- what
+ * point_measurement(f, g) (src/bldfm/utils.py:80-92) computes per footprint on the host.
+ *   weight        host [ny][nx] float64 (e.g. the surface flux map)
+ *   conc_w, flx_w host [nprob][nlv] float64. */
+int  bldfm_solve_batched_measure(bldfm_plan *plan, int32_t nprob, const bldfm_problem *probs,
+                                 const int64_t *levels, int32_t nlv, const double *srf_flx, int flags,
+                                 const double *weight, double *conc_w, double *flx_w);
+
 /* One OVERSIZED problem sharded by ky-slab over `nranks` GPUs (one process per GPU); replaces nothing
  * in the reference -- it scales a single steady_state_transport_solver call (src/bldfm/solver.py:16)
  * beyond one device.  Footprint mode, float64.  Every rank calls

@@ -137,7 +137,7 @@ def wavenumbers(g):
 
 def solve(srf_flx, z, profiles, domain, levels, modes=(512, 512), meas_pt=(0.0, 0.0),
           srf_bg_conc=0.0, footprint=False, analytic=False, halo=None, precision="single",
-          nthreads: int = 1, return_spectral: bool = False):
+          nthreads: int = 1, return_spectral: bool = False, alpha_scale: float = 1.0):
     """Restatement of ``steady_state_transport_solver`` (solver.py:16-304) without the cache.
 
     Returns ((X, Y, Z), conc, flx) exactly like the reference (np.squeeze'd).
@@ -204,6 +204,8 @@ def solve(srf_flx, z, profiles, domain, levels, modes=(512, 512), meas_pt=(0.0, 
         p2, q2, P2, Q2 = ivp((zero, tq0[msk]), profiles, z, lv, Lxm, Lym, nthreads)
         # --- K6: shooting coefficient and combination (solver.py:228-235)
         alpha = -(q2 - Kz[nz - 1] * eig * p2) / (q1 - Kz[nz - 1] * eig * p1)
+        if alpha_scale != 1.0:            # self-noise probe, never used in parity
+            alpha = alpha * alpha_scale
         tp[:, msk] = alpha * P1 + P2
         tq[:, msk] = alpha * Q1 + Q2
         # --- K7: degenerate mode by trapezoid (solver.py:239-251)

@@ -84,3 +84,24 @@ def test_batch_shares_marches_between_towers(gpu_lib):
     for i, pt in enumerate(pts):
         _, c1, f1 = bldfm_b200.steady_state_transport_solver(np.zeros((64, 64)), z, prof, meas_pt=pt, **kw)
         assert np.array_equal(conc[i, 0], c1) and np.array_equal(flx[i, 0], f1)
+
+
+def test_measure_batched_equals_point_measurement(gpu_lib):
+    """f-4: footprint x flux-map sums on the device == point_measurement on the host fields."""
+    import bldfm_b200
+    from bldfm_b200.pbl_model import vertical_profiles
+    from bldfm_b200.utils import ideal_source, point_measurement
+    dom = (960.0, 720.0)
+    flux_map = ideal_source((64, 48), dom, shape="circle") + 0.1
+    zs, profs, pts = [], [], []
+    for i in range(5):
+        z, p = vertical_profiles(16, 10.0, (3.0 + 0.2 * i, -2.0), ustar=0.4, mol=-60.0 - 10 * i)
+        zs.append(z); profs.append(p); pts.append((300.0 + 40 * i, 350.0))
+    kw = dict(domain=dom, levels=[8, 16], modes=(64, 48), footprint=True, precision="double")
+    conc, flx = bldfm_b200.solve_batched(np.zeros((48, 64)), zs, profs, meas_pts=pts, **kw)
+    cw, fw = bldfm_b200.measure_batched(flux_map, np.zeros((48, 64)), zs, profs, meas_pts=pts, **kw)
+    assert cw.shape == (5, 2) and fw.shape == (5, 2)
+    for b in range(5):
+        for l in range(2):
+            assert abs(fw[b, l] - point_measurement(flx[b, l], flux_map)) <= 1e-12 * abs(fw[b, l])
+            assert abs(cw[b, l] - point_measurement(conc[b, l], flux_map)) <= 1e-12 * abs(cw[b, l])
