@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib
 
-MAX_OUTSTANDING = int(os.environ.get("BLDFM_B200_PINNED_MAX", str(512 << 20)))
+MAX_OUTSTANDING = int(os.environ.get("BLDFM_B200_PINNED_MAX", str(4 << 30)))
 _GRAIN = 1 << 16
 
 

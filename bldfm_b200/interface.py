@@ -24,7 +24,7 @@ from .utils import compute_wind_fields, ideal_source
 
 logger = logging.getLogger("bldfm.interface")
 
-MAX_CHUNK_BYTES = 512 << 20   # host bytes of (conc, flx) per batched launch
+MAX_CHUNK_BYTES = 256 << 20   # host bytes of (conc, flx) per batched launch
 
 
 def _make_cache(config):
