@@ -106,7 +106,14 @@ struct bldfm_plan {
     DevBuf src_in, src_pad;  // non-footprint: device copy of srf_flx, padded complex / spectrum
     DevBuf fft_work;         // pruned path: intermediate [field][nly][nx]
     DevBuf tw64, tw32;       // pruned path: twiddle tables  x[nfx] | y[nfy]  (double2 / float2)
-    DevBuf out_c, out_f;     // device outputs when the caller wants host results
+    DevBuf out_c, out_f;     // device outputs when the caller wants host results (set 0)
+    DevBuf out_c2, out_f2;   // second set: D2H of one solve overlaps the compute of the next
+    int out_set = 0;
+    cudaStream_t copy_stream = nullptr;       // D2H of results runs here
+    cudaEvent_t compute_done = nullptr;
+    cudaEvent_t copy_done[2] = {nullptr, nullptr};
+    bool copy_pending[2] = {false, false};
+    uint64_t weight_sig = 0;                  // signature of the weight map held in `weight`
     DevBuf weight, partial;  // f-4 weighted sums: weight map [ny][nx], partial sums | results
     Staging staging[kStagingSlots];
     int staging_next = 0;
@@ -601,10 +608,23 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     const int64_t out_per_field = (int64_t)g.nx * g.ny;
     void* d_conc = out.conc;
     void* d_flx = out.flx;
+    int oset = 0;
     if (!out_dev) {
-        TRY(pl->out_c.ensure((size_t)nfields * out_per_field * relem));
-        TRY(pl->out_f.ensure((size_t)nfields * out_per_field * relem));
-        d_conc = pl->out_c.p; d_flx = pl->out_f.p;
+        oset = pl->out_set;
+        pl->out_set ^= 1;
+        DevBuf& bc = oset ? pl->out_c2 : pl->out_c;
+        DevBuf& bf = oset ? pl->out_f2 : pl->out_f;
+        // this set's previous D2H (on the copy stream) must be done before it is overwritten; if the
+        // buffers have to grow, cudaFree would race with it -> drain the copy stream first
+        const size_t need = (size_t)nfields * out_per_field * relem;
+        if (pl->copy_pending[oset]) {
+            if (need > bc.cap || need > bf.cap) CUDA_TRY(cudaStreamSynchronize(pl->copy_stream));
+            else CUDA_TRY(cudaStreamWaitEvent(pl->stream, pl->copy_done[oset], 0));
+            pl->copy_pending[oset] = false;
+        }
+        TRY(bc.ensure(need));
+        TRY(bf.ensure(need));
+        d_conc = bc.p; d_flx = bf.p;
     }
     const bool forward_dir = footprint;   // fft2(norm="backward") vs ifft2(norm="forward")  solver.py:280-287
     const bool use_library = (flags & BLDFM_FFT_LIBRARY) || !pruned_fft_supported(g, spec_f32, pl->smem_optin);
@@ -681,12 +701,27 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev[3], pl->stream));
 
     if (!out_dev) {
+        // results leave on the copy stream so that the next solve's kernels can start meanwhile
         const size_t nb = (size_t)nfields * out_per_field * relem;
-        CUDA_TRY(cudaMemcpyAsync(out.conc, d_conc, nb, cudaMemcpyDeviceToHost, pl->stream));
-        CUDA_TRY(cudaMemcpyAsync(out.flx, d_flx, nb, cudaMemcpyDeviceToHost, pl->stream));
+        CUDA_TRY(cudaEventRecord(pl->compute_done, pl->stream));
+        CUDA_TRY(cudaStreamWaitEvent(pl->copy_stream, pl->compute_done, 0));
+        CUDA_TRY(cudaMemcpyAsync(out.conc, d_conc, nb, cudaMemcpyDeviceToHost, pl->copy_stream));
+        CUDA_TRY(cudaMemcpyAsync(out.flx, d_flx, nb, cudaMemcpyDeviceToHost, pl->copy_stream));
+        CUDA_TRY(cudaEventRecord(pl->copy_done[oset], pl->copy_stream));
+        pl->copy_pending[oset] = true;
+        if (pl->profiling) {
+            CUDA_TRY(cudaStreamWaitEvent(pl->stream, pl->copy_done[oset], 0));
+            CUDA_TRY(cudaEventRecord(pl->ev[4], pl->stream));
+            pl->ev_recorded = true;
+        }
+        if (!(flags & BLDFM_ASYNC)) {
+            CUDA_TRY(cudaStreamSynchronize(pl->copy_stream));
+            pl->copy_pending[oset] = false;
+        }
+        return BLDFM_OK;
     }
     if (pl->profiling) { CUDA_TRY(cudaEventRecord(pl->ev[4], pl->stream)); pl->ev_recorded = true; }
-    if (!out_dev || !(flags & BLDFM_ASYNC)) CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    if (!(flags & BLDFM_ASYNC)) CUDA_TRY(cudaStreamSynchronize(pl->stream));
     return BLDFM_OK;
 }
 
@@ -815,6 +850,11 @@ int bldfm_plan_create(const bldfm_geometry* g, int device, bldfm_plan** out)
         e = cudaEventCreate(&ev);
         if (e != cudaSuccess) { bldfm_plan_destroy(pl); return fail(BLDFM_ERR_CUDA, cudaGetErrorString(e)); }
     }
+    e = cudaStreamCreateWithFlags(&pl->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->compute_done, cudaEventDisableTiming);
+    for (auto& ev : pl->copy_done)
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) { bldfm_plan_destroy(pl); return fail(BLDFM_ERR_CUDA, cudaGetErrorString(e)); }
     // wavenumber tables
     std::vector<double> tab((size_t)g->nlx + g->nly);
     bldfm_wavenumbers(g, tab.data(), tab.data() + g->nlx);
@@ -831,7 +871,12 @@ int bldfm_plan_destroy(bldfm_plan* pl)
     if (!pl) return BLDFM_OK;
     DeviceGuard guard(pl->device);
     if (pl->stream) cudaStreamSynchronize(pl->stream);
+    if (pl->copy_stream) cudaStreamSynchronize(pl->copy_stream);
     for (auto& kv : pl->fft_plans) cufftDestroy(kv.second);
+    pl->out_c2.release(); pl->out_f2.release();
+    if (pl->compute_done) cudaEventDestroy(pl->compute_done);
+    for (auto& ev : pl->copy_done) if (ev) cudaEventDestroy(ev);
+    if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
     pl->tables.release(); pl->params.release(); pl->spec_p.release(); pl->spec_q.release();
     pl->pad_in.release(); pl->pad_out.release(); pl->src_in.release(); pl->src_pad.release();
     pl->weight.release(); pl->partial.release();
@@ -853,6 +898,8 @@ int bldfm_plan_synchronize(bldfm_plan* pl)
     if (!pl) return fail(BLDFM_ERR_INVALID, "plan is NULL");
     DeviceGuard guard(pl->device);
     CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    CUDA_TRY(cudaStreamSynchronize(pl->copy_stream));
+    pl->copy_pending[0] = pl->copy_pending[1] = false;
     return BLDFM_OK;
 }
 
@@ -886,7 +933,7 @@ int64_t bldfm_plan_workspace_bytes(const bldfm_plan* pl)
     if (!pl) return 0;
     return (int64_t)(pl->tables.cap + pl->params.cap + pl->spec_p.cap + pl->spec_q.cap + pl->pad_in.cap +
                      pl->pad_out.cap + pl->src_in.cap + pl->src_pad.cap + pl->fft_work.cap +
-                     pl->out_c.cap + pl->out_f.cap);
+                     pl->out_c.cap + pl->out_f.cap + pl->out_c2.cap + pl->out_f2.cap);
 }
 
 int bldfm_solve(bldfm_plan* plan, const bldfm_problem* prob, const int64_t* levels, int32_t nlv,
@@ -929,7 +976,20 @@ int bldfm_solve_batched_measure(bldfm_plan* pl, int32_t nprob, const bldfm_probl
     TRY(pl->out_f.ensure((size_t)nfields * per_field * relem));
     TRY(pl->weight.ensure((size_t)per_field * sizeof(double)));
     TRY(pl->partial.ensure((size_t)2 * nfields * (kReduceBlocks + 1) * sizeof(double)));
-    CUDA_TRY(cudaMemcpyAsync(pl->weight.p, weight, (size_t)per_field * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+    {
+        // upload the weight map only when it changed: signature = pointer, size and 1024 samples
+        uint64_t sig = fnv1a(&weight, sizeof(weight), 1469598103934665603ull);
+        sig = fnv1a(&per_field, sizeof(per_field), sig);
+        const int64_t stride = std::max<int64_t>(1, per_field / 1024);
+        for (int64_t i = 0; i < per_field; i += stride) sig = fnv1a(weight + i, sizeof(double), sig);
+        sig = fnv1a(weight + per_field - 1, sizeof(double), sig);
+        if (sig != pl->weight_sig) {
+            CUDA_TRY(cudaMemcpyAsync(pl->weight.p, weight, (size_t)per_field * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+            pl->weight_sig = sig;
+        }
+    }
+    for (int k = 0; k < 2; ++k)
+        if (pl->copy_pending[k]) { CUDA_TRY(cudaStreamWaitEvent(pl->stream, pl->copy_done[k], 0)); }
     SolveOut o; o.conc = pl->out_c.p; o.flx = pl->out_f.p;
     if (nfields > 32767) return fail(BLDFM_ERR_INVALID, "too many fields in one measurement batch (max 32767)");
     const int f2 = flags | BLDFM_OUT_ON_DEVICE | BLDFM_ASYNC;

@@ -19,12 +19,12 @@ import numpy as np
 
 from . import distributed as _dist
 from .pbl_model import vertical_profiles
-from .solver import make_grid, solve_batched, steady_state_transport_solver
+from .solver import make_grid, solve_batched, steady_state_transport_solver, synchronize
 from .utils import compute_wind_fields, ideal_source
 
 logger = logging.getLogger("bldfm.interface")
 
-MAX_CHUNK_BYTES = 256 << 20   # host bytes of (conc, flx) per batched launch
+MAX_CHUNK_BYTES = 128 << 20   # host bytes of (conc, flx) per batched launch
 
 
 def _make_cache(config):
@@ -136,12 +136,18 @@ def solve_tasks(config, tasks: Sequence[Tuple[int, int]], surface_flux=None, cac
     nlv = len(lv)
     per_problem = 2 * nlv * dom.ny * dom.nx * 8
     chunk = max(1, min(256, MAX_CHUNK_BYTES // max(per_problem, 1)))
+    # enqueue every chunk without waiting: the device->host copy of chunk k overlaps the kernels of
+    # chunk k+1 and the host-side profile work of the chunks after it
+    inflight = []
     for c0 in range(0, len(pending), chunk):
         part = pending[c0:c0 + chunk]
         conc, flx = solve_batched(
             srf, [p[3] for p in part], [p[4] for p in part], domain, levels, modes=dom.modes,
             meas_pts=[(p[1].x, p[1].y) for p in part], footprint=sol.footprint, analytic=sol.analytic,
-            halo=dom.halo, precision=sol.precision)
+            halo=dom.halo, precision=sol.precision, wait=False)
+        inflight.append((part, conc, flx))
+    synchronize()
+    for part, conc, flx in inflight:
         for b, (t, tower, met_step, z, profiles) in enumerate(part):
             grid = make_grid(z, lv, domain, dom.nx, dom.ny)
             res = (grid, np.squeeze(conc[b]), np.squeeze(flx[b]))

@@ -139,13 +139,17 @@ def steady_state_transport_solver(
 
 
 def solve_batched(srf_flx, zs, profiles_list, domain, levels, modes=(512, 512), meas_pts=None,
-                  srf_bg_conc=0.0, footprint=False, analytic=False, halo=None, precision="single"):
+                  srf_bg_conc=0.0, footprint=False, analytic=False, halo=None, precision="single",
+                  wait=True):
     """Many (tower, met) conditions in ONE launch (C entry point ``bldfm_solve_batched``).
 
     ``zs[b]``, ``profiles_list[b]``, ``meas_pts[b]`` describe problem b; everything else is shared.
     Problems with byte-identical (z, profiles) share one vertical march.  Returns
     ``(conc, flx)`` of shape ``[B, nlv, ny, nx]`` (float32 only for precision="single" without any
     phase shift, like the single-problem solver).
+
+    ``wait=False`` only enqueues the work: the returned arrays (pinned host memory) are valid after
+    ``synchronize()``; the device->host copy of this batch then overlaps the kernels of the next one.
     """
     q0 = np.asarray(srf_flx)
     ny, nx = q0.shape
@@ -174,11 +178,20 @@ def solve_batched(srf_flx, zs, profiles_list, domain, levels, modes=(512, 512), 
     src = None if footprint else _lib.as_f64(q0)
     parr = (_lib.Problem * B)(*probs)
     plan = get_fft_manager().plan(geom)
+    if not wait:
+        flags |= _lib.ASYNC
     _lib.check(_lib.lib().bldfm_solve_batched(
         plan, B, parr, lv64.ctypes.data_as(C.POINTER(C.c_int64)), nlv,
         None if src is None else _lib.ptr(src), flags, _lib.ptr(conc), _lib.ptr(flx)))
     del keep
     return conc, flx
+
+
+def synchronize():
+    """Wait for every enqueued solve / result copy on this process's plans (after ``wait=False``)."""
+    mgr = get_fft_manager()
+    for h in list(mgr._plans.values()):
+        _lib.check(_lib.lib().bldfm_plan_synchronize(h))
 
 
 def measure_batched(weight, srf_flx, zs, profiles_list, domain, levels, modes=(512, 512), meas_pts=None,

@@ -42,7 +42,10 @@ extern "C" {
 #define BLDFM_MARCH_FMA        0x008  /* opt-in: FMA-contracted march (faster, not bit-mirrored)                 */
 #define BLDFM_SRC_ON_DEVICE    0x010  /* srf_flx is a device pointer                                              */
 #define BLDFM_OUT_ON_DEVICE    0x020  /* conc/flx are device pointers                                             */
-#define BLDFM_ASYNC            0x040  /* with BLDFM_OUT_ON_DEVICE: enqueue on the plan's stream, do not sync      */
+#define BLDFM_ASYNC            0x040  /* enqueue only, do not synchronise.  Device outputs: ordered on the plan's
+                                         stream.  Host outputs: they must be PINNED and may be read only after
+                                         bldfm_plan_synchronize(); the D2H of one solve then overlaps the next
+                                         solve's kernels (double-buffered device results, separate copy stream) */
 #define BLDFM_FFT_LIBRARY      0x080  /* force the cuFFT transform path instead of the pruned in-house kernels    */
 #define BLDFM_FFT_FULL         0x100  /* in-house back-transform without the real-output (Hermitian) halving      */
 
