@@ -215,6 +215,48 @@ __device__ __forceinline__ void fft_stage(typename Vec2<T>::type* buf, const typ
     }
 }
 
+// Generic prime radix (7, 11, 13) as a MIDDLE stage: each thread produces one output
+//   y[i0 + q*L] = sum_u x[i0 + u*L] * w^(u*(j*step + q*N/R)),   w = exp(-2*pi*i/N)
+// with O(R) table twiddles, out of place (src -> dst halves of the shared buffer).  O(N*R) work for
+// this one stage -- it exists so that padded sizes with a factor 7/11/13 (e.g. halo 500 m on a
+// 0.39 m grid: 2816 = 2^8*11, 5376 = 2^8*3*7) stay on the in-house pruned path.
+template <typename T>
+__device__ __forceinline__ void fft_stage_generic(const typename Vec2<T>::type* src, typename Vec2<T>::type* dst,
+                                                  const typename Vec2<T>::type* __restrict__ tw, int N, int L,
+                                                  int R, int cw)
+{
+    using V = typename Vec2<T>::type;
+    const int LR = L * R;
+    const int step = N / LR;
+    const int nr = N / R;
+    const int total = cw * N;
+    for (int e = threadIdx.x; e < total; e += (int)blockDim.x) {
+        const int t = (int)((unsigned)e / (unsigned)N);
+        const int i = e - t * N;
+        const int blk = (int)((unsigned)i / (unsigned)LR);
+        const int rem = i - blk * LR;
+        const int q = (int)((unsigned)rem / (unsigned)L);
+        const int j = rem - q * L;
+        const int i0 = blk * LR + j;
+        int base = j * step + q * nr;
+        if (base >= N) base -= N * (base / N);
+        const V* p = src + (size_t)t * fft_stride(N);
+        Cplx<T> acc = {(T)0, (T)0};
+        int idx = 0;
+        for (int u = 0; u < R; ++u) {
+            const V x = p[fft_swz(i0 + u * L)];
+            const V w = tw[idx];
+            acc.r = xfma<T>(x.x, w.x, xfma<T>(-x.y, w.y, acc.r));
+            acc.i = xfma<T>(x.x, w.y, xfma<T>(x.y, w.x, acc.i));
+            idx += base;
+            if (idx >= N) idx -= N;
+        }
+        dst[(size_t)t * fft_stride(N) + fft_swz(i)] = mk2<T>(acc.r, acc.i);
+    }
+}
+
+__device__ __forceinline__ bool fft_is_generic(int r) { return r == 7 || r > 8; }
+
 // grid = (ceil(ntrans/cw), nfields) ; block = fft_pick_threads() ; dynamic smem = cw*(N+pad)*sizeof(complex)
 template <typename T, bool REAL_IN, bool REAL_OUT>
 __global__ void __launch_bounds__(kFftMaxThreads, 2)
@@ -250,18 +292,24 @@ k_fft_pass(const FftPassArgs a)
     __syncthreads();
 
     const V* tw = reinterpret_cast<const V*>(a.twiddle);
+    V* other = buf + (size_t)a.cw * fft_stride(N);     // second half, only present for generic radices
     int L = 1;
     for (int s = 0; s < a.nstages; ++s) {
         const int r = a.radix[s];
         // the last stage only needs to keep what the output window will read
         const bool last = (s == a.nstages - 1) && !a.out_freq;
         const int lo = last ? a.out_off : 0, hi = last ? a.out_off + a.n_out : N;
-        switch (r) {
-            case 2: fft_stage<T, 2>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
-            case 3: fft_stage<T, 3>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
-            case 4: fft_stage<T, 4>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
-            case 5: fft_stage<T, 5>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
-            default: fft_stage<T, 8>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
+        if (fft_is_generic(r)) {
+            fft_stage_generic<T>(buf, other, tw, N, L, r, cw);
+            V* tmp = buf; buf = other; other = tmp;
+        } else {
+            switch (r) {
+                case 2: fft_stage<T, 2>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
+                case 3: fft_stage<T, 3>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
+                case 4: fft_stage<T, 4>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
+                case 5: fft_stage<T, 5>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
+                default: fft_stage<T, 8>(buf, tw, N, L, a.lshift[s], cw, lo, hi); break;
+            }
         }
         L *= r;
         __syncthreads();
@@ -297,19 +345,34 @@ k_fft_pass(const FftPassArgs a)
 inline bool fft_factorize(int n, std::vector<int>& radix)
 {
     radix.clear();
-    if (n < 1) return false;
+    if (n < 2) return false;
     // powers of two first: the sub-transform length L stays a power of two (shift/mask indexing)
-    // until the 3s and 5s come in at the end.
-    std::vector<int> pow2, odd;
-    while (n % 8 == 0) { pow2.push_back(8); n /= 8; }
-    while (n % 4 == 0) { pow2.push_back(4); n /= 4; }
-    while (n % 2 == 0) { pow2.push_back(2); n /= 2; }
+    // until the 3s and 5s come in at the end; generic primes (7, 11, 13) go in the middle because
+    // the first and the last stage are specialised (register-resident) for radices 2,3,4,5,8.
+    std::vector<int> pool, generic, odd;
+    while (n % 8 == 0) { pool.push_back(8); n /= 8; }
+    while (n % 4 == 0) { pool.push_back(4); n /= 4; }
+    while (n % 2 == 0) { pool.push_back(2); n /= 2; }
     while (n % 3 == 0) { odd.push_back(3); n /= 3; }
     while (n % 5 == 0) { odd.push_back(5); n /= 5; }
+    for (int p : {7, 11, 13})
+        while (n % p == 0) { generic.push_back(p); n /= p; }
     if (n != 1) return false;
-    radix = pow2;
-    radix.insert(radix.end(), odd.begin(), odd.end());
+    pool.insert(pool.end(), odd.begin(), odd.end());
+    if (generic.empty()) {
+        radix = pool;
+    } else {
+        if (pool.size() < 2) return false;
+        radix.assign(pool.begin(), pool.end() - 1);
+        radix.insert(radix.end(), generic.begin(), generic.end());
+        radix.push_back(pool.back());
+    }
     return !radix.empty() && (int)radix.size() <= kFftMaxStages;
+}
+
+inline bool fft_has_generic(int n)
+{
+    return n % 7 == 0 || n % 11 == 0 || n % 13 == 0;
 }
 
 // fills radix[], lshift[] of a pass
@@ -344,7 +407,9 @@ inline void fft_rev_table(int N, const std::vector<int>& radix, std::vector<int3
 
 inline size_t fft_smem_bytes(int N, int cw, bool f32)
 {
-    return (size_t)cw * (size_t)fft_stride(N) * (f32 ? sizeof(float2) : sizeof(double2));
+    // sizes with a generic-radix stage need a second (out-of-place) half
+    return (size_t)(fft_has_generic(N) ? 2 : 1) * (size_t)cw * (size_t)fft_stride(N) *
+           (f32 ? sizeof(float2) : sizeof(double2));
 }
 
 inline int fft_env_int(const char* name, int dflt)

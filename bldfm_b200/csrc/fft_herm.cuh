@@ -227,15 +227,21 @@ k_fft_h(const FftHArgs a)
     }
     if (a.nstages == 1) return;
     __syncthreads();
+    V* other = buf + (size_t)a.cw * fft_stride(N);     // second half, only present for generic radices
     int L = a.radix[0];
     for (int s = 1; s < a.nstages - 1; ++s) {
         const int r = a.radix[s];
-        switch (r) {
-            case 2: fft_stage<T, 2>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
-            case 3: fft_stage<T, 3>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
-            case 4: fft_stage<T, 4>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
-            case 5: fft_stage<T, 5>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
-            default: fft_stage<T, 8>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
+        if (fft_is_generic(r)) {
+            fft_stage_generic<T>(buf, other, tw, N, L, r, cw);
+            V* tmp = buf; buf = other; other = tmp;
+        } else {
+            switch (r) {
+                case 2: fft_stage<T, 2>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
+                case 3: fft_stage<T, 3>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
+                case 4: fft_stage<T, 4>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
+                case 5: fft_stage<T, 5>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
+                default: fft_stage<T, 8>(buf, tw, N, L, a.lshift[s], cw, 0, N); break;
+            }
         }
         L *= r;
         __syncthreads();

@@ -229,6 +229,9 @@ def test_cache_roundtrip(B, tmp_path):
     ((24, 40), (16, 8), 35.0),        # truncated modes, small halo
     ((2, 2), (2, 2), None),           # smallest grid
     ((15, 45), (512, 512), 0.0),      # odd sizes 3^2*5 x 3*5, modes clamped to odd counts, in-house path
+    ((88, 56), (56, 88), 0.0),        # generic-radix stages: 56 = 8*7, 88 = 8*11, no truncation
+    ((44, 28), (16, 20), 126.0),      # padded 56 x 66 = (8*7) x (2*3*11), truncated modes
+    ((208, 208), (64, 48), 0.0),      # 208 = 16*13
     ((33, 21), (512, 512), 50.0),     # odd sizes, modes clamped; 7 and 11 as factors -> library fallback
 ])
 def test_edge_geometries_against_oracle(B, oracle, shape, modes, halo, fft):
