@@ -130,7 +130,7 @@ def lib():
         "bldfm_memcpy_h2d": (C.c_int, [C.c_int, vp, vp, i64]),
         "bldfm_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, _DP]),
         "bldfm_solve_batched_measure": (C.c_int, [vp, i32, PP, I64P, i32, vp, C.c_int, vp, vp, vp]),
-        "bldfm_sharded_stage1": (C.c_int, [vp, PP, I64P, i32, C.c_int, i32, i32, vp, vp, vp, vp]),
+        "bldfm_sharded_stage1": (C.c_int, [vp, PP, I64P, i32, vp, C.c_int, i32, i32, vp, vp, vp, vp]),
         "bldfm_sharded_stage2": (C.c_int, [vp, i32, C.c_int, i32, i32, vp, vp, vp, vp]),
         "bldfm_ipc_export": (C.c_int, [vp, C.c_char_p]),
         "bldfm_ipc_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(vp)]),

@@ -355,7 +355,6 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     int ky0 = 0, rows = g.nly;
     if (sh) {
         if (nprob != 1) return fail(BLDFM_ERR_INVALID, "sharded solve takes one problem");
-        if (!footprint) return fail(BLDFM_ERR_INVALID, "sharded solve supports footprint mode only (non-footprint: not built yet)");
         if (sh->nranks < 1 || sh->rank < 0 || sh->rank >= sh->nranks) return fail(BLDFM_ERR_INVALID, "bad rank / nranks");
         if (g.nly % sh->nranks || g.nx % sh->nranks)
             return fail(BLDFM_ERR_INVALID, "sharded solve needs nly and nx divisible by the number of ranks");
@@ -492,8 +491,8 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
                                      cudaMemcpyHostToDevice, pl->stream));
             d_q0 = static_cast<const double*>(pl->src_in.p);
         }
-        const bool lib_fwd = (flags & BLDFM_FFT_LIBRARY) || !pruned_fft_supported(g, false, pl->smem_optin) ||
-                             g.nfx != g.nxe || g.nfy != g.nye;
+        const bool lib_fwd = !sh && ((flags & BLDFM_FFT_LIBRARY) || !pruned_fft_supported(g, false, pl->smem_optin) ||
+                                     g.nfx != g.nxe || g.nfy != g.nye);
         if (lib_fwd) {
             TRY(pl->src_pad.ensure(sizeof(double2) * (size_t)g.nxe * g.nye));
             double2* d_pad = static_cast<double2*>(pl->src_pad.p);
@@ -508,13 +507,14 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         } else {
             // pruned: [ny][nlx] intermediate + compact [nly][nlx] spectrum
             const size_t wbytes = sizeof(double2) * (size_t)g.ny * g.nlx;
-            const size_t sbytes = sizeof(double2) * (size_t)g.nly * g.nlx;
+            const size_t sbytes = sizeof(double2) * (size_t)rows * g.nlx;
             TRY(pl->src_pad.ensure(wbytes + sbytes));
             char* base = static_cast<char*>(pl->src_pad.p);
             PrunedFftTables tab;
             TRY(ensure_twiddles(pl, false, &tab));
             int nl = 0;
-            cudaError_t fe = pruned_fft_forward(pl->stream, pl->smem_optin, g, d_q0, base, base + wbytes, tab, &nl);
+            cudaError_t fe = pruned_fft_forward(pl->stream, pl->smem_optin, g, d_q0, base, base + wbytes, tab, &nl,
+                                                ky0, rows);
             if (fe != cudaSuccess) return fail(BLDFM_ERR_CUDA, std::string("pruned forward FFT: ") + cudaGetErrorString(fe));
             pl->launches += nl;
             d_src_spec = reinterpret_cast<const double2*>(base + wbytes);
@@ -541,6 +541,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         a.src_pitch = src_compact ? g.nlx : g.nxe;
         a.src_nfx = src_compact ? g.nlx : g.nxe;
         a.src_nfy = src_compact ? g.nly : g.nye;
+        a.src_ky0 = src_compact ? ky0 : 0;
         a.q0_const = 1.0 / g.nxe / g.nye;                           // solver.py:134
         a.src_scale = 1.0 / ((double)g.nxe * (double)g.nye);        // norm="forward"
         a.src_spec = d_src_spec;
@@ -1021,14 +1022,14 @@ int bldfm_solve_spectral(bldfm_plan* plan, const bldfm_problem* prob, const int6
 }
 
 int bldfm_sharded_stage1(bldfm_plan* plan, const bldfm_problem* prob, const int64_t* levels, int32_t nlv,
-                         int flags, int32_t rank, int32_t nranks, void* send_p, void* send_q,
+                         const double* srf_flx, int flags, int32_t rank, int32_t nranks, void* send_p, void* send_q,
                          void* const* peer_p, void* const* peer_q)
 {
     Shard sh;
     sh.rank = rank; sh.nranks = nranks; sh.send_p = send_p; sh.send_q = send_q;
     sh.peer_p = peer_p; sh.peer_q = peer_q;
     SolveOut o;
-    return solve_impl(plan, 1, prob, levels, nlv, nullptr, flags | BLDFM_OUT_ON_DEVICE, o, &sh);
+    return solve_impl(plan, 1, prob, levels, nlv, srf_flx, flags | BLDFM_OUT_ON_DEVICE, o, &sh);
 }
 
 int bldfm_sharded_stage2(bldfm_plan* pl, int32_t nlv, int flags, int32_t rank, int32_t nranks,

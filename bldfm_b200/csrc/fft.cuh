@@ -43,6 +43,9 @@ struct FftPassArgs {
     // outputs: out_freq ? n_out entries in fftfreq order : the window [out_off, out_off + n_out)
     int32_t in_freq, n_in, in_off;
     int32_t out_freq, n_out, out_off;
+    // with out_freq: output j is entry (out_foff + j) of an fftfreq-ordered set of out_ftotal entries
+    // (out_ftotal = 0 means the n_out entries are the whole set)
+    int32_t out_ftotal, out_foff;
     int32_t cw;                // transforms per CTA
     int32_t ntrans;            // transforms per field
     int32_t t_fast;            // 1: consecutive threads walk the transform index first
@@ -316,12 +319,14 @@ k_fft_pass(const FftPassArgs a)
     }
 
     // store the requested outputs
-    const int npos_out = (a.n_out + 1) / 2;
+    const int ftotal = a.out_ftotal > 0 ? a.out_ftotal : a.n_out;
+    const int npos_out = (ftotal + 1) / 2;
     for (int e = threadIdx.x; e < cw * a.n_out; e += (int)blockDim.x) {
         int t, j;
         if (a.t_fast) { j = e / cw; t = e - j * cw; }
         else          { t = e / a.n_out; j = e - t * a.n_out; }
-        const int i = a.out_freq ? (j < npos_out ? j : j - a.n_out + N) : a.out_off + j;
+        const int kk = j + a.out_foff;
+        const int i = a.out_freq ? (kk < npos_out ? kk : kk - ftotal + N) : a.out_off + j;
         const V x = buf[(size_t)t * fft_stride(N) + fft_swz(i)];
         size_t o = field * a.out_field_stride + (size_t)(t0 + t) * a.out_tstride;
         void* dst = outp;
@@ -628,8 +633,9 @@ inline cudaError_t sharded_ypass(cudaStream_t stream, size_t smem_optin, const b
 // `work` holds [ny][nlx] c128.  Two launches.
 inline cudaError_t pruned_fft_forward(cudaStream_t stream, size_t smem_optin, const bldfm_geometry& g,
                                       const double* q0, void* work, void* spec, const PrunedFftTables& tab,
-                                      int* nlaunch)
+                                      int* nlaunch, int ky0 = 0, int rows = -1)
 {
+    if (rows < 0) rows = g.nly;      // ky-slab sharding: only rows [ky0, ky0+rows) of the spectrum
     std::vector<int> rx, ry;
     fft_factorize(g.nxe, rx);
     fft_factorize(g.nye, ry);
@@ -644,7 +650,8 @@ inline cudaError_t pruned_fft_forward(cudaStream_t stream, size_t smem_optin, co
 
     FftPassArgs ay{};
     ay.N = g.nye; fft_set_stages(ay, ry); ay.rev = tab.rev_y;
-    ay.in_freq = 0; ay.n_in = g.ny; ay.in_off = g.py; ay.out_freq = 1; ay.n_out = g.nly; ay.out_off = 0;
+    ay.in_freq = 0; ay.n_in = g.ny; ay.in_off = g.py; ay.out_freq = 1; ay.n_out = rows; ay.out_off = 0;
+    ay.out_ftotal = g.nly; ay.out_foff = ky0;
     ay.cw = fft_pick_cw(g.nye, false, smem_optin, 4);
     ay.ntrans = g.nlx; ay.t_fast = 1; ay.conj_io = 0;
     ay.in_field_stride = 0; ay.in_tstride = 1; ay.in_kstride = g.nlx;

@@ -152,6 +152,7 @@ struct MarchArgs {
     int32_t footprint;
     int32_t src_pitch;         // row pitch (complex elements) of src_spec
     int32_t src_nfx, src_nfy;  // size of the forward spectrum for index wrapping
+    int32_t src_ky0;           // first ky row held by src_spec (ky-slab sharding), else 0
     double  q0_const;          // (1/nxe)/nye                                   solver.py:134
     double  src_scale;         // 1/(nxe*nye)   norm="forward"                  solver.py:136
     const double2*   src_spec; // forward spectrum of the padded source (non-footprint)
@@ -256,7 +257,7 @@ k_march(const MarchArgs a)
         const int pk = (a.nlx + 1) / 2, pl = (a.nly + 1) / 2;
         const int wx = kx < pk ? kx : kx - a.nlx + a.src_nfx;
         const int wy = ky < pl ? ky : ky - a.nly + a.src_nfy;
-        const double2 sv = a.src_spec[(size_t)wy * a.src_pitch + wx];
+        const double2 sv = a.src_spec[(size_t)(wy - a.src_ky0) * a.src_pitch + wx];
         q0r = sv.x * a.src_scale; q0i = sv.y * a.src_scale;
     }
 
@@ -386,7 +387,7 @@ k_analytic(const MarchArgs a)
         const int pk = (a.nlx + 1) / 2, pl = (a.nly + 1) / 2;
         const int wx = kx < pk ? kx : kx - a.nlx + a.src_nfx;
         const int wy = ky < pl ? ky : ky - a.nly + a.src_nfy;
-        const double2 sv = a.src_spec[(size_t)wy * a.src_pitch + wx];
+        const double2 sv = a.src_spec[(size_t)(wy - a.src_ky0) * a.src_pitch + wx];
         q0r = sv.x * a.src_scale; q0i = sv.y * a.src_scale;
     }
     const Emit emit(a, gd, mode, lx, ly);

@@ -11,7 +11,10 @@ Every rank (one process per GPU, ``torch.distributed`` initialised with NCCL) ca
      mapped pointers, so the transpose rides on the kernel's own stores;
   3. y-transforms its ``nx/G`` columns into real slabs (``bldfm_sharded_stage2``).
 
-The slabs are optionally all-gathered into the full fields.  Footprint mode, float64.
+The slabs are optionally all-gathered into the full fields.  float64.  In non-footprint mode every rank
+holds the whole source and computes only its own rows of the source spectrum (the x-pass over the ny
+source rows is replicated on every rank -- about 1 % of the march work -- so the forward transform
+needs no exchange at all).
 """
 
 from __future__ import annotations
@@ -98,8 +101,6 @@ def steady_state_transport_solver_sharded(srf_flx, z, profiles, domain, levels, 
     import torch
     import torch.distributed as dist
 
-    if not footprint:
-        raise NotImplementedError("sharded solve: only footprint mode is built")
     if precision != "double":
         raise ValueError("sharded solve: precision must be 'double'")
     rank, G = world()
@@ -108,7 +109,9 @@ def steady_state_transport_solver_sharded(srf_flx, z, profiles, domain, levels, 
     q0 = np.asarray(srf_flx)
     ny, nx = q0.shape
     geom = _geometry(q0.shape, domain, modes, halo)
-    flags = _flags(True, False, precision) | _lib.ASYNC
+    flags = _flags(footprint, False, precision) | _lib.ASYNC
+    src = None if footprint else _lib.as_f64(q0)
+    srcp = None if src is None else _lib.ptr(src)
     lv, lv64 = _levels_array(levels)
     nlv = len(lv64)
     if geom.nly % G or nx % G:
@@ -132,7 +135,7 @@ def steady_state_transport_solver_sharded(srf_flx, z, profiles, domain, levels, 
                                dtype=torch.int64, device=device)
             send = torch.empty(1, dtype=torch.complex128, device=device)    # unused placeholder
             dist.barrier()                                                 # peers finished reading (WAR)
-            _lib.check(L.bldfm_sharded_stage1(plan, C.byref(prob), lvp, nlv, flags, rank, G,
+            _lib.check(L.bldfm_sharded_stage1(plan, C.byref(prob), lvp, nlv, srcp, flags, rank, G,
                                               send.data_ptr(), send.data_ptr(),
                                               tab[0].data_ptr(), tab[1].data_ptr()))
             stream.synchronize()                                           # my stores have landed
@@ -140,7 +143,7 @@ def steady_state_transport_solver_sharded(srf_flx, z, profiles, domain, levels, 
             recv_p, recv_q = pb.local
         else:
             send = torch.empty((2, nlv, G, rows, nxl), dtype=torch.complex128, device=device)
-            _lib.check(L.bldfm_sharded_stage1(plan, C.byref(prob), lvp, nlv, flags, rank, G,
+            _lib.check(L.bldfm_sharded_stage1(plan, C.byref(prob), lvp, nlv, srcp, flags, rank, G,
                                               send[0].data_ptr(), send[1].data_ptr(), None, None))
             if G > 1:
                 recv = torch.empty_like(send)

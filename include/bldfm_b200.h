@@ -148,7 +148,9 @@ int  bldfm_solve_batched_measure(bldfm_plan *plan, int32_t nprob, const bldfm_pr
 
 /* One OVERSIZED problem sharded by ky-slab over `nranks` GPUs (one process per GPU); replaces nothing
  * in the reference -- it scales a single steady_state_transport_solver call (src/bldfm/solver.py:16)
- * beyond one device.  Footprint mode, float64.  Every rank calls
+ * beyond one device.  float64.  In non-footprint mode every rank holds the whole source srf_flx and computes only
+ * its own rows of the source spectrum (the x-pass over the ny source rows is replicated -- ~1 % of the march --
+ * so the forward side needs no exchange).  Every rank calls
  *   stage1: march + x-transform of the retained rows [rank*nly/G, (rank+1)*nly/G); results go to the
  *           device buffers send_p/send_q laid out [nlv][dst][nly/G][nx/G] complex128, ready for an
  *           all-to-all (done by the caller, e.g. torch.distributed over NCCL) -- or, when peer_p/peer_q
@@ -158,7 +160,7 @@ int  bldfm_solve_batched_measure(bldfm_plan *plan, int32_t nprob, const bldfm_pr
  *           conc_slab/flx_slab [nlv][ny][nx/G] float64 (device).
  * Both stages are enqueued on the plan's stream; BLDFM_ASYNC skips the final synchronisation. */
 int  bldfm_sharded_stage1(bldfm_plan *plan, const bldfm_problem *prob, const int64_t *levels, int32_t nlv,
-                          int flags, int32_t rank, int32_t nranks, void *send_p, void *send_q,
+                          const double *srf_flx, int flags, int32_t rank, int32_t nranks, void *send_p, void *send_q,
                           void *const *peer_p, void *const *peer_q);
 int  bldfm_sharded_stage2(bldfm_plan *plan, int32_t nlv, int flags, int32_t rank, int32_t nranks,
                           const void *recv_p, const void *recv_q, void *conc_slab, void *flx_slab);

@@ -12,11 +12,14 @@ from conftest import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def _problem(n=96, nz=16):
+def _problem(n=96, nz=16, footprint=True):
     from bldfm_b200.pbl_model import vertical_profiles
+    from bldfm_b200.utils import ideal_source
     z, prof = vertical_profiles(nz, 10.0, (-3.0, -4.0), ustar=0.4, mol=-50.0)
-    return dict(srf_flx=np.zeros((n, n)), z=z, profiles=prof, domain=(n * 7.8125, n * 7.8125),
-                levels=[3, nz], modes=(n, n), meas_pt=(n * 3.9, n * 3.1), footprint=True, precision="double")
+    dom = (n * 7.8125, n * 7.8125)
+    src = np.zeros((n, n)) if footprint else ideal_source((n, n), dom, src_loc=(dom[0] * 0.6, dom[1] * 0.7), shape="circle")
+    return dict(srf_flx=src, z=z, profiles=prof, domain=dom, levels=[3, nz], modes=(n, n),
+                meas_pt=(n * 3.9, n * 3.1), footprint=footprint, precision="double")
 
 
 def test_sharded_world1_equals_plain(gpu_lib):
@@ -37,8 +40,15 @@ def test_sharded_world1_equals_plain(gpu_lib):
     assert np.abs(f2 - f1).max() <= 1e-13 * np.abs(f1).max()
     for a, b in zip(g0, g1):
         assert np.array_equal(a, b)
-    with pytest.raises(NotImplementedError):
-        steady_state_transport_solver_sharded(**{**kw, "footprint": False})
+    # non-footprint: the rank computes its rows of the source spectrum itself
+    kw = _problem(footprint=False)
+    bldfm_b200.config.FFT_FULL = True
+    try:
+        _, c0, f0 = bldfm_b200.steady_state_transport_solver(**kw)
+    finally:
+        bldfm_b200.config.FFT_FULL = False
+    _, c1, f1 = steady_state_transport_solver_sharded(**kw)
+    assert np.array_equal(c0, c1) and np.array_equal(f0, f1)
 
 
 def _free_port():
@@ -59,11 +69,17 @@ def _worker(rank, world, port, q):
         import bldfm_b200
         from bldfm_b200.sharded import release_peer_buffers, steady_state_transport_solver_sharded
         bldfm_b200.config.DEVICE = rank
+        res = {}
+        kwn = _problem(footprint=False)
+        bldfm_b200.config.FFT_FULL = True
+        _, c0, f0 = bldfm_b200.steady_state_transport_solver(**kwn)
+        bldfm_b200.config.FFT_FULL = False
+        _, c1, f1 = steady_state_transport_solver_sharded(**kwn)
+        res["non-footprint"] = bool(np.array_equal(c0, c1) and np.array_equal(f0, f1))
         kw = _problem()
         bldfm_b200.config.FFT_FULL = True
         _, c0, f0 = bldfm_b200.steady_state_transport_solver(**kw)
         bldfm_b200.config.FFT_FULL = False
-        res = {}
         for fused in (False, True):
             for rep in range(2):
                 _, c1, f1 = steady_state_transport_solver_sharded(fused=fused, **kw)
