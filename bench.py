@@ -356,7 +356,7 @@ def main():
             "batched": {"batch": B, "ms_per_batch": batch_ms, "solves_per_s": world * B / (batch_ms * 1e-3),
                         "mode_levels_per_s": world * B / (batch_ms * 1e-3) * mode_levels},
         }
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:
             from oracle import bldfm_oracle as O
             cores = O.max_threads()
             sps, ms = cpu_reference_leg({**kw}, 4, 1, cores)

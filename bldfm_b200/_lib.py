@@ -73,8 +73,11 @@ _DP = C.POINTER(C.c_double)
 
 
 class Problem(C.Structure):
+    # the six profile pointers are declared void* (same ABI as const double*): plain integer
+    # addresses can be assigned without a ctypes cast, which is what dominates the per-call cost
     _fields_ = [
-        ("z", _DP), ("u", _DP), ("v", _DP), ("Kx", _DP), ("Ky", _DP), ("Kz", _DP),
+        ("z", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("Kx", C.c_void_p), ("Ky", C.c_void_p),
+        ("Kz", C.c_void_p),
         ("nz", C.c_int32), ("reserved", C.c_int32),
         ("xm", C.c_double), ("ym", C.c_double), ("srf_bg_conc", C.c_double),
     ]
@@ -193,19 +196,30 @@ def dptr(a):
     return a.ctypes.data_as(_DP)
 
 
+def _f64c(a):
+    """float64 C-contiguous view/copy with a fast path for arrays that already are."""
+    if type(a) is np.ndarray and a.dtype == np.float64 and a.flags.c_contiguous:
+        return a
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
 def make_problem(z, profiles, meas_pt, srf_bg_conc):
-    """Build a Problem struct; returns (struct, keepalive) -- keep `keepalive` referenced."""
-    z = as_f64(z)
-    arrs = [as_f64(a) for a in profiles]
-    if len(arrs) != 5:
+    """Build a Problem struct; returns (struct, keepalive) -- keep `keepalive` referenced.
+
+    z and the five profiles are packed into ONE [6][nz] float64 buffer: taking the address of a
+    numpy array from Python costs ~2.5 us, six of them would dominate the call.
+    """
+    if len(profiles) != 5:
         raise ValueError("profiles must be (u, v, Kx, Ky, Kz)")
-    for a in arrs:
-        if a.shape != z.shape:
-            raise ValueError("profiles must have the same length as z")
-    p = Problem()
-    p.z = dptr(z)
-    p.u, p.v, p.Kx, p.Ky, p.Kz = (dptr(a) for a in arrs)
-    p.nz = z.shape[0]
-    p.xm, p.ym = float(meas_pt[0]), float(meas_pt[1])
-    p.srf_bg_conc = float(srf_bg_conc)
-    return p, (z, arrs)
+    n = len(z)
+    buf = np.empty((6, n), dtype=np.float64)
+    try:
+        buf[0] = z
+        buf[1], buf[2], buf[3], buf[4], buf[5] = profiles
+    except ValueError:
+        raise ValueError("profiles must have the same length as z") from None
+    base = buf.ctypes.data
+    row = n * 8
+    p = Problem(base, base + row, base + 2 * row, base + 3 * row, base + 4 * row, base + 5 * row, n, 0,
+                float(meas_pt[0]), float(meas_pt[1]), float(srf_bg_conc))
+    return p, buf

@@ -24,20 +24,35 @@ class PlanManager:
         self.num_threads = num_threads
         self.cache_keepalive = cache_keepalive
         self._plans = {}
+        self._memo_owners = []
         self._pid = os.getpid()
+
+    def _forget_memos(self):
+        for g in self._memo_owners:
+            g.__dict__.pop("_plans", None)
+        self._memo_owners = []
 
     def plan(self, geom: _lib.Geometry, device: int | None = None):
         if os.getpid() != self._pid:
             # forked child: the parent's CUDA context is unusable here -- forget, never destroy
             self._plans = {}
+            self._forget_memos()
             self._pid = os.getpid()
         dev = config.DEVICE if device is None else int(device)
+        # fast path: the handle is remembered on the (cached) Geometry object itself
+        memo = geom.__dict__.get("_plans")
+        if memo is not None:
+            hit = memo.get((id(self), dev))
+            if hit is not None:
+                return hit
         key = (dev,) + geom.key()
         h = self._plans.get(key)
         if h is None:
             h = C.c_void_p()
             _lib.check(_lib.lib().bldfm_plan_create(C.byref(geom), dev, C.byref(h)))
             self._plans[key] = h
+        geom.__dict__.setdefault("_plans", {})[(id(self), dev)] = h
+        self._memo_owners.append(geom)
         return h
 
     def clear_cache(self):
@@ -45,6 +60,7 @@ class PlanManager:
             for h in self._plans.values():
                 _lib.lib().bldfm_plan_destroy(h)
         self._plans = {}
+        self._forget_memos()
 
     def launch_count(self) -> int:
         return sum(int(_lib.lib().bldfm_plan_launch_count(h)) for h in self._plans.values())

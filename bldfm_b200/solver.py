@@ -56,25 +56,53 @@ def _geometry(shape, domain, modes, halo):
     return g
 
 
+_LEVEL_CACHE = {}
+
+
 def _levels_array(levels):
-    lv = np.array([levels]) if np.ndim(levels) == 0 else np.asarray(levels)   # solver.py:102-103
+    """(levels as the reference indexes with them, int64 copy for the C side)   solver.py:102-103"""
+    if type(levels) is int:
+        hit = _LEVEL_CACHE.get(levels)
+        if hit is None:
+            lv = np.array([levels])
+            hit = (lv, np.ascontiguousarray(lv, dtype=np.int64))
+            if len(_LEVEL_CACHE) < 1024:
+                _LEVEL_CACHE[levels] = hit
+        return hit
+    lv = np.array([levels]) if np.ndim(levels) == 0 else np.asarray(levels)
+    if lv.dtype.kind not in "iub":
+        # numpy refuses float arrays as indices (z[levels], solver.py:296)
+        raise IndexError("arrays used as indices must be of integer (or boolean) type")
     return lv, np.ascontiguousarray(lv, dtype=np.int64)
+
+
+_XY_CACHE = {}
 
 
 def make_grid(z, lv, domain, nx, ny):
     """(X, Y, Z) of solver.py:293-298.  Values/shapes as the reference; see config.GRID_COPY."""
     xmx, ymx = domain
-    x = np.linspace(0, xmx, nx, endpoint=False)
-    y = np.linspace(0, ymx, ny, endpoint=False)
     zl = np.asarray(z)[lv]
     if config.GRID_COPY:
+        x = np.linspace(0, xmx, nx, endpoint=False)
+        y = np.linspace(0, ymx, ny, endpoint=False)
         Z, Y, X = np.meshgrid(zl, y, x, indexing="ij")
-    else:
-        shape = (len(zl), ny, nx)
-        Z = np.broadcast_to(zl[:, None, None], shape)
-        Y = np.broadcast_to(y[None, :, None], shape)
-        X = np.broadcast_to(x[None, None, :], shape)
-    return np.squeeze(X), np.squeeze(Y), np.squeeze(Z)
+        return np.squeeze(X), np.squeeze(Y), np.squeeze(Z)
+    nlv = len(zl)
+    key = (float(xmx), float(ymx), nx, ny, nlv)
+    xy = _XY_CACHE.get(key)
+    if xy is None:
+        x = np.linspace(0, xmx, nx, endpoint=False)
+        y = np.linspace(0, ymx, ny, endpoint=False)
+        x.setflags(write=False)
+        y.setflags(write=False)
+        shape = (nlv, ny, nx)
+        xy = (np.squeeze(np.broadcast_to(x[None, None, :], shape)),
+              np.squeeze(np.broadcast_to(y[None, :, None], shape)))
+        if len(_XY_CACHE) < 64:
+            _XY_CACHE[key] = xy
+    Z = np.squeeze(np.broadcast_to(zl[:, None, None], (nlv, ny, nx)))
+    return xy[0], xy[1], Z
 
 
 def steady_state_transport_solver(
@@ -117,8 +145,8 @@ def steady_state_transport_solver(
     prob, keep = _lib.make_problem(z, profiles, meas_pt, srf_bg_conc)
     f32 = bool(_lib.lib().bldfm_output_is_f32(flags, prob.xm, prob.ym))
     dt = np.float32 if f32 else np.float64
-    conc = _pinned_pool.empty((nlv, ny, nx), dt)
-    flx = _pinned_pool.empty((nlv, ny, nx), dt)
+    both = _pinned_pool.empty((2, nlv, ny, nx), dt)
+    conc, flx = both[0], both[1]
     src = None
     if not footprint:
         src = _lib.as_f64(q0)
