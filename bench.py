@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="problems per launch for the extra batched figure")
+    ap.add_argument("--batch", type=int, default=32, help="problems per launch for the extra batched figure")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
 
@@ -280,9 +280,9 @@ def main():
     from bldfm_b200.pbl_model import vertical_profiles
     probs, keeps = [], []
     for b in range(B):
-        zb, pb = vertical_profiles(64, 10.0, (-3.0 - 0.05 * b, -4.0 + 0.03 * b), ustar=0.4, mol=-50.0 - b)
-        if len(zb) != len(kw["z"]):
-            zb, pb = kw["z"], kw["profiles"]
+        # B DISTINCT met conditions (distinct profiles => B separate marches, nothing is shared)
+        zb, pb = vertical_profiles(64, 10.0, (-3.0 - 0.02 * b, -4.0 + 0.01 * b), ustar=0.4 + 0.001 * b,
+                                   mol=-50.0 - 0.5 * b)
         p_, k_ = _lib.make_problem(zb, pb, kw["meas_pt"], 0.0)
         probs.append(p_)
         keeps.append(k_)
@@ -328,7 +328,7 @@ def main():
                        "l2": "flushed with a 256 MiB memset between timed steps"},
             "mode_levels_per_s": value * mode_levels,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
-                    "h2d_bytes_per_step": int(S * 128 + 64 + 24 + (S + 1) * 4),
+                    "h2d_bytes_per_step": int(S * 128 + 80 + 24 + (S + 1) * 4),   # coef | group | tower | row_of
                     "d2h_bytes_per_step": int(2 * 512 * 512 * 8),
                     "ms_per_step_median_rank0": float(np.median(e2e_calls)) * 1e3,
                     "ms_per_step_p90_rank0": float(np.percentile(e2e_calls, 90)) * 1e3,

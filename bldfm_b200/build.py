@@ -49,7 +49,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     cuda_lib = Path(_nvcc()).resolve().parent.parent / "lib64"
     cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", str(LIB), *map(str, sources()),
            "-I", str(PKG.parent / "include"),
-           "-L", str(cuda_lib), "-lcufft",
+           "-L", str(cuda_lib), "-lcufft", "-ldl",
            "-Xlinker", f"-rpath={cuda_lib}"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")

@@ -7,6 +7,7 @@
 
 #include <cufft.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges show up in ncu / nsys when a tool is attached
 
 #include <algorithm>
 #include <cmath>
@@ -53,6 +54,11 @@ int fail(int code, const std::string& msg)
         int rc__ = (expr);           \
         if (rc__ != BLDFM_OK) return rc__; \
     } while (0)
+
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct DevBuf {
     void* p = nullptr;
@@ -480,6 +486,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     CUDA_TRY(cudaEventRecord(st->done, pl->stream));
     st->in_flight = true;
 
+    NvtxRange nvtx_solve("bldfm_solve");
     // ---- K1-K3: spectrum of the padded source (non-footprint)
     const double2* d_src_spec = nullptr;
     bool src_compact = false;
@@ -524,6 +531,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev[1], pl->stream));
 
     // ---- K4-K8: fused march -> compact spectra
+    nvtxMarkA("bldfm:march");
     const int64_t nmodes = (int64_t)g.nlx * rows;
     const int64_t nfields = (int64_t)nprob * nlv;
     TRY(pl->spec_p.ensure((size_t)nfields * nmodes * celem));
@@ -606,6 +614,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     }
 
     // ---- K9-K11: back-transform + crop
+    nvtxMarkA("bldfm:back-transform");
     const int64_t out_per_field = (int64_t)g.nx * g.ny;
     void* d_conc = out.conc;
     void* d_flx = out.flx;

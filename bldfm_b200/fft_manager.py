@@ -47,13 +47,24 @@ class PlanManager:
                 return hit
         key = (dev,) + geom.key()
         h = self._plans.get(key)
+        if h is not None:
+            self._plans[key] = self._plans.pop(key)        # most recently used goes last
         if h is None:
+            self._evict_if_needed()
             h = C.c_void_p()
             _lib.check(_lib.lib().bldfm_plan_create(C.byref(geom), dev, C.byref(h)))
             self._plans[key] = h
         geom.__dict__.setdefault("_plans", {})[(id(self), dev)] = h
         self._memo_owners.append(geom)
         return h
+
+    def _evict_if_needed(self):
+        """Destroy least-recently-used plans while the cached workspaces exceed the budget."""
+        L = _lib.lib()
+        while len(self._plans) > 0 and self.workspace_bytes() > config.MAX_WORKSPACE_BYTES:
+            key = next(iter(self._plans))
+            L.bldfm_plan_destroy(self._plans.pop(key))
+            self._forget_memos()
 
     def clear_cache(self):
         if os.getpid() == self._pid:

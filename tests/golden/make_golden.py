@@ -13,6 +13,7 @@ reference's imports; no reference file is modified or cop
   solve_*.npz    inputs + outputs of bldfm.solver.steady_state_transport_solver for small cases
                  (incl. the scenarios behind the reference's own tests/references/*.npz)
   refgold.npz    the reference's regression goldens source_area / plume_3d (conc, flx only)
+  cache_keys.json  GreensFunctionCache keys of the reference for fixed inputs (byte-identity pin)
 """
 
 from __future__ import annotations
@@ -153,6 +154,24 @@ def gen_solves():
     (HERE / "index.json").write_text(json.dumps(index, indent=1, sort_keys=True))
 
 
+def gen_cache_keys():
+    """Reference cache keys (bldfm.cache.GreensFunctionCache._compute_key) for fixed inputs."""
+    import tempfile
+
+    from bldfm.cache import GreensFunctionCache
+
+    cache = GreensFunctionCache(cache_dir=tempfile.mkdtemp())
+    z, profs = vertical_profiles(16, 10.0, (0.0, -6.0), 0.5)
+    keys = {}
+    for i, (domain, modes, meas_pt, halo, prec) in enumerate([
+            ((100.0, 700.0), (64, 128), (50.0, 0.0), None, "single"),
+            ((100.0, 700.0), (64, 128), (50.0, 0.0), 200.0, "double"),
+            ((4000.0, 4000.0), (512, 512), (2000, 2000), None, "double")]):
+        keys[str(i)] = dict(domain=domain, modes=modes, meas_pt=meas_pt, halo=halo, precision=prec,
+                            key=cache._compute_key(z, profs, domain, modes, meas_pt, halo, prec))
+    (HERE / "cache_keys.json").write_text(json.dumps(keys, indent=1))
+
+
 def gen_refgold():
     out = {}
     for name in ("source_area", "plume_3d"):
@@ -168,3 +187,4 @@ if __name__ == "__main__":
     gen_profiles()
     gen_solves()
     gen_refgold()
+    gen_cache_keys()

@@ -96,3 +96,30 @@ def test_profile_errors():
         vertical_profiles(8, 10.0, (1.0, 0.0), ustar=0.3, z0=0.1)
     with pytest.raises(ValueError, match="Invalid closure type"):
         vertical_profiles(8, 10.0, (1.0, 0.0), ustar=0.3, closure="NOPE")
+
+
+def test_cache_keys_identical_to_reference():
+    """GreensFunctionCache keys must stay byte-identical to the reference's (cache.py:36-47)."""
+    from bldfm_b200.cache import GreensFunctionCache, cache_key
+    from bldfm_b200.pbl_model import vertical_profiles
+    keys = json.loads((GOLDEN / "cache_keys.json").read_text())
+    z, profs = vertical_profiles(16, 10.0, (0.0, -6.0), 0.5)
+    for rec in keys.values():
+        args = (z, profs, tuple(rec["domain"]), tuple(rec["modes"]), tuple(rec["meas_pt"]), rec["halo"], rec["precision"])
+        assert cache_key(*args) == rec["key"]
+
+
+def test_cache_put_get_clear(tmp_path):
+    from bldfm_b200.cache import GreensFunctionCache
+    c = GreensFunctionCache(cache_dir=tmp_path / "cc")
+    z = np.linspace(0.1, 20, 9)
+    profs = tuple(z * (i + 1) for i in range(5))
+    args = (z, profs, (10.0, 20.0), (8, 8), (1.0, 2.0), None, "single")
+    assert c.get(*args) is None
+    grid = (np.ones((4, 4)), np.zeros((4, 4)), np.full((4, 4), 2.0))
+    c.put(*args, grid, np.arange(16.0).reshape(4, 4), -np.arange(16.0).reshape(4, 4))
+    g, conc, flx = c.get(*args)
+    assert np.array_equal(conc, np.arange(16.0).reshape(4, 4)) and np.array_equal(g[2], grid[2])
+    assert c.get(z, profs, (10.0, 20.0), (8, 8), (1.0, 2.5), None, "single") is None
+    c.clear()
+    assert c.get(*args) is None
