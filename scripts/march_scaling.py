@@ -35,4 +35,5 @@ for mode in ("exact", "fma"):
     S = np.array([r[0] for r in rows], float)
     T = np.array([r[1] for r in rows], float)
     b, a = np.polyfit(S, T, 1)
-    print(json.dumps({"mode": mode, "steps_ms": rows, "fixed_us": a * 1e3, "per_step_us": b * 1e3}))
+    print(json.dumps({"mode": mode, "fixed_us": round(a * 1e3, 2), "per_step_us": round(b * 1e3, 4),
+                      "S104_ms": rows[3][1], "steps_ms": rows}))
