@@ -133,8 +133,8 @@ def run_reference(args, rank, world):
     O.build()
     kw = config2()
     cores = O.max_threads()
-    steps = max(1, min(args.steps, 12))
-    warm = max(1, min(args.warmup, 2))
+    steps = max(1, min(args.steps, 60))       # bounded: ~0.1 s per solve on 16 cores
+    warm = max(1, min(args.warmup, 3))
     sps, ms = cpu_reference_leg(kw, steps, warm, cores)
     g = O.geometry(kw["srf_flx"].shape, kw["domain"], kw["modes"], None)
     mode_levels = (g["nlx"] * g["nly"] - 1) * (len(kw["z"]) - 1)
@@ -359,9 +359,9 @@ def main():
         if not args.no_cpu and world == 1:
             from oracle import bldfm_oracle as O
             cores = O.max_threads()
-            sps, ms = cpu_reference_leg({**kw}, 4, 1, cores)
+            sps, ms = cpu_reference_leg({**kw}, 24, 2, cores)
             line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "4 full config-2 solves (oracle port: pthread C march + scipy.fft, all host threads)",
+                                    "sample": "24 full config-2 solves (oracle port: pthread C march + scipy.fft, all host threads)",
                                     "ms_per_step": ms}
         print(json.dumps(line))
     if world > 1:
