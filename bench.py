@@ -12,8 +12,8 @@ weak scaling); time = max over ranks; value = N*K / time.
             stream, L2 flushed (256 MiB memset) between steps.
   e2e       same metric through the public Python API `steady_state_transport_solver` with host
             numpy inputs/outputs (H2D of the staged profiles, D2H of conc+flx inside the timing).
-  roofline  the dominant kernel (fused march): algorithmic flops 86*M*S / measured
-            kernel time, against the FP64 pipe rate measured in this run by a DADD/DMUL (exact
+  roofline  the dominant kernel (fused march): 86 flops per marched mode-step (the
+            kernel marches the conjugate-symmetric half of the M modes) / measured kernel time, against the FP64 pipe rate measured in this run by a DADD/DMUL (exact
             mode) or DFMA (fma mode) micro-benchmark; the HBM view is given alongside.
   cpu_baseline  the oracle port (C march with all host threads + scipy.fft) on the same config.
 
@@ -52,6 +52,11 @@ def config2():
 WORKLOAD = ("BASELINE config 2: single-tower footprint 512x512, n=64 (105 levels, 104 march steps), "
             "modes 512x512, halo=4000 m (padded 1536x1536), unstable MOST (ustar=0.4, L=-50 m, "
             "wind (-3,-4)), level z_m, FP64")
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_march on this workload, from the committed
+# `ncu --set full` captures under profiles/ (key: march mode, full-plane march)
+NCU_TRAFFIC = {("exact", True): 84736}
 
 
 class ClockSampler:
@@ -199,6 +204,8 @@ def main():
     flags = _lib.FOOTPRINT | _lib.DOUBLE | _lib.OUT_ON_DEVICE | _lib.ASYNC | (_lib.MARCH_FMA if fma_mode else 0)
     if bldfm_b200.config.FFT_LIBRARY:
         flags |= _lib.FFT_LIBRARY
+    if bldfm_b200.config.MARCH_FULL:
+        flags |= _lib.MARCH_FULL
 
     plan = bldfm_b200.get_fft_manager().plan(geom, local)
     stream = torch.cuda.ExternalStream(L.bldfm_plan_stream(plan), device=local)
@@ -315,7 +322,11 @@ def main():
     if rank == 0:
         value = world * args.steps / (dev_ms * 1e-3)
         e2e = world * args.steps / (e2e_ms * 1e-3)
-        flops = 86.0 * M * S
+        # modes actually marched: the half-plane ky <= nly/2 plus the lower half of the Nyquist column
+        # (conjugate symmetry of a real source's spectra, march.cuh); the reference marches all M
+        full_march = bldfm_b200.config.MARCH_FULL
+        M_run = M if full_march else geom.nlx * (geom.nly // 2 + 1) + (geom.nly - 1) // 2 - 1
+        flops = 86.0 * M_run * S
         achieved = flops / (march_ms * 1e-3) * 1e-12
         peak = (peak_ops.value * (2.0 if fma_mode else 1.0)) * 1e-3        # TFLOP/s
         alg_bytes = 2 * geom.nlx * geom.nly * 16 + S * 128
@@ -343,8 +354,11 @@ def main():
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
                 # capture of this kernel on this workload (profiles/r1a_march_exact_ncu.txt): the 8.4 MB
                 # of spectra it writes stay in the 126 MB L2 for the transform that follows
-                "traffic": 84736 if not fma_mode else None,
+                "traffic": NCU_TRAFFIC.get((bldfm_b200.config.MARCH_MODE, full_march)),
                 "flops_per_launch": flops, "kernel_ms": march_ms,
+                "modes_marched": M_run, "modes_retained": M,
+                # the same launch counted with SURVEY.md 8d's figure 86*M*S (what the reference executes)
+                "reference_count_tflops": 86.0 * M * S / (march_ms * 1e-3) * 1e-12,
                 "peak_source": ("measured in this run: bldfm_fp64_peak "
                                 + ("DFMA x2" if fma_mode else "DADD/DMUL (non-fused ops, exact mode)")),
                 "peak_dfma_tflops": peak_fma.value * 2e-3,

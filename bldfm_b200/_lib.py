@@ -35,6 +35,7 @@ OUT_ON_DEVICE = 0x020
 ASYNC = 0x040
 FFT_LIBRARY = 0x080
 FFT_FULL = 0x100
+MARCH_FULL = 0x200
 
 # every symbol include/bldfm_b200.h declares (tests check the library exports all of them)
 EXPORTS = [

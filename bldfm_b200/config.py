@@ -24,6 +24,8 @@ GRID_COPY = os.environ.get("BLDFM_B200_GRID_COPY", "0") == "1"
 FFT_LIBRARY = os.environ.get("BLDFM_B200_FFT_LIBRARY", "0") == "1"
 # Use the full complex pruned passes instead of the real-output (Hermitian) half-work passes.
 FFT_FULL = os.environ.get("BLDFM_B200_FFT_FULL", "0") == "1"
+# March every retained mode instead of the half-plane whose conjugates fill the rest (cross-check).
+MARCH_FULL = os.environ.get("BLDFM_B200_MARCH_FULL", "0") == "1"
 # Device workspace budget over all cached plans of this process [bytes]; least-recently-used plans
 # are destroyed when a new plan would be created above it (a 1024^2 x 129-level plan holds ~9 GB).
 MAX_WORKSPACE_BYTES = int(os.environ.get("BLDFM_B200_MAX_WORKSPACE", str(64 << 30)))

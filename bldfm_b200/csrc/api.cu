@@ -536,6 +536,11 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     const int64_t nfields = (int64_t)nprob * nlv;
     TRY(pl->spec_p.ensure((size_t)nfields * nmodes * celem));
     TRY(pl->spec_q.ensure((size_t)nfields * nmodes * celem));
+    if (spectral) {
+        // parity export: poison the spectra (NaN) so that a mode the march fails to write shows up
+        CUDA_TRY(cudaMemsetAsync(pl->spec_p.p, 0xFF, (size_t)nfields * nmodes * celem, pl->stream));
+        CUDA_TRY(cudaMemsetAsync(pl->spec_q.p, 0xFF, (size_t)nfields * nmodes * celem, pl->stream));
+    }
     {
         char* dbase = static_cast<char*>(pl->params.p);
         MarchArgs a{};
@@ -546,6 +551,8 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         a.single = dbl ? 0 : 1;
         a.out_f32 = spec_f32 ? 1 : 0;
         a.footprint = footprint ? 1 : 0;
+        // conjugate symmetry of the spectra of a real source: march half the modes (march.cuh)
+        a.herm = (!sh && !(flags & BLDFM_MARCH_FULL)) ? 1 : 0;
         a.src_pitch = src_compact ? g.nlx : g.nxe;
         a.src_nfx = src_compact ? g.nlx : g.nxe;
         a.src_nfy = src_compact ? g.nly : g.nye;
@@ -562,7 +569,8 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         a.outp = pl->spec_p.p; a.outq = pl->spec_q.p;
         a.slot_stride = (int64_t)nlv * nmodes;
 
-        const dim3 grid((unsigned)((nmodes + kMarchThreads - 1) / kMarchThreads), (unsigned)ngroups);
+        const int64_t nthreads = march_thread_count(g.nlx, rows, g.nly, a.herm != 0);
+        const dim3 grid((unsigned)((nthreads + kMarchThreads - 1) / kMarchThreads), (unsigned)ngroups);
         const size_t smem = (size_t)coef_stride * sizeof(LevelCoef) + (size_t)nz_max * sizeof(int32_t);
         if (smem > pl->smem_optin)
             return fail(BLDFM_ERR_INVALID, "nz too large for the shared-memory coefficient table (" +

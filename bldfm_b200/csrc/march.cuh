@@ -150,6 +150,7 @@ struct MarchArgs {
     int32_t single;            // precision == "single": round tfftp/tfftq to complex64 values
     int32_t out_f32;           // spectra stored as float2 (no shift applied, single)
     int32_t footprint;
+    int32_t herm;              // 1: march only the half-plane ky <= nly/2 and store the conjugate mirror
     int32_t src_pitch;         // row pitch (complex elements) of src_spec
     int32_t src_nfx, src_nfy;  // size of the forward spectrum for index wrapping
     int32_t src_ky0;           // first ky row held by src_spec (ky-slab sharding), else 0
@@ -174,12 +175,13 @@ struct Emit {
     const GroupDesc& gd;
     const TowerDesc* tw;
     int64_t mode;
+    int64_t mirror;      // index of the mode (-ky,-kx) that receives the conjugate, or -1
     double lx, ly;
     double cs0, sn0;     // phase factor of the group's first tower, hoisted out of the row loop
 
     __device__ __forceinline__ Emit(const MarchArgs& a_, const GroupDesc& gd_, int64_t mode_,
-                                    double lx_, double ly_)
-        : a(a_), gd(gd_), tw(a_.towers + gd_.tow_begin), mode(mode_), lx(lx_), ly(ly_),
+                                    int64_t mirror_, double lx_, double ly_)
+        : a(a_), gd(gd_), tw(a_.towers + gd_.tow_begin), mode(mode_), mirror(mirror_), lx(lx_), ly(ly_),
           cs0(1.0), sn0(0.0)
     {
         if (gd.tow_count > 0 && tw[0].shift) phase(tw[0], cs0, sn0);
@@ -199,7 +201,8 @@ struct Emit {
         if (a.single) {
             pr = round_f32(pr); pi = round_f32(pi); qr = round_f32(qr); qi = round_f32(qi);
         }
-        const int64_t rowoff = (int64_t)row * a.nly_loc * a.nlx + mode;
+        const int64_t rowbase = (int64_t)row * a.nly_loc * a.nlx;
+        const int64_t rowoff = rowbase + mode;
         for (int t = 0; t < gd.tow_count; ++t) {
             const TowerDesc td = tw[t];
             double opr = pr, opi = pi, oqr = qr, oqi = qi;
@@ -217,9 +220,70 @@ struct Emit {
                 reinterpret_cast<double2*>(a.outp)[o] = make_double2(opr, opi);
                 reinterpret_cast<double2*>(a.outq)[o] = make_double2(oqr, oqi);
             }
+            if (mirror >= 0) {
+                // mode (-ky,-kx): every operation of the march, the radiation condition and the
+                // phase factor is sign-symmetric in the imaginary parts, so the reference's value
+                // there is the exact complex conjugate (bit for bit)
+                const int64_t om = (int64_t)td.slot * a.slot_stride + rowbase + mirror;
+                if (a.out_f32) {
+                    reinterpret_cast<float2*>(a.outp)[om] = make_float2((float)opr, -(float)opi);
+                    reinterpret_cast<float2*>(a.outq)[om] = make_float2((float)oqr, -(float)oqi);
+                } else {
+                    reinterpret_cast<double2*>(a.outp)[om] = make_double2(opr, -opi);
+                    reinterpret_cast<double2*>(a.outq)[om] = make_double2(oqr, -oqi);
+                }
+            }
         }
     }
 };
+
+// Thread -> mode map.  Full plane: one thread per retained mode of rows ky0 .. ky0+nly_loc-1.
+// Half plane (herm): T(-k) = conj(T(k)), both initial states are conjugate-symmetric for a real source,
+// hence state(-k) = conj(state(k)): only rows ky = 0 .. nly/2 are marched and each thread also stores
+// the conjugate at (-ky,-kx).  Modes without a partner in the retained set are marched on their own:
+// row 0 (its partner is in the same row; marched in full), the Nyquist row ky = nly/2 and the Nyquist
+// column kx = nlx/2 (even sizes; fftfreq keeps only -n/2) -- the latter's lower half by extra threads
+// appended after the half-plane.
+struct ModeMap { int ky, kx; int64_t mode, mirror; };
+
+__host__ __device__ __forceinline__ int64_t march_thread_count(int nlx, int nly_loc, int nly, bool herm)
+{
+    if (!herm) return (int64_t)nlx * nly_loc;
+    const int nmir = (nly - 1) / 2;                        // rows 1..nmir have a partner row nly-ky
+    return (int64_t)nlx * (nly / 2 + 1) + ((nlx % 2 == 0) ? nmir : 0);
+}
+
+__device__ __forceinline__ bool march_map(const MarchArgs& a, int64_t tid, ModeMap& m)
+{
+    if (!a.herm) {
+        if (tid >= (int64_t)a.nlx * a.nly_loc) return false;
+        const int kyl = (int)(tid / a.nlx);
+        m.kx = (int)(tid - (int64_t)kyl * a.nlx);
+        m.ky = a.ky0 + kyl;
+        m.mode = tid;
+        m.mirror = -1;
+        return true;
+    }
+    const int nrow = a.nly / 2 + 1;
+    const int nmir = (a.nly - 1) / 2;
+    const bool even_x = (a.nlx % 2) == 0;
+    const int64_t nmain = (int64_t)a.nlx * nrow;
+    if (tid < nmain) {
+        m.ky = (int)(tid / a.nlx);
+        m.kx = (int)(tid - (int64_t)m.ky * a.nlx);
+        m.mode = tid;
+        const bool has = m.ky >= 1 && m.ky <= nmir && !(even_x && m.kx == a.nlx / 2);
+        m.mirror = has ? (int64_t)(a.nly - m.ky) * a.nlx + (m.kx == 0 ? 0 : a.nlx - m.kx) : -1;
+        return true;
+    }
+    const int64_t e = tid - nmain;
+    if (!even_x || e >= nmir) return false;
+    m.ky = nrow + (int)e;
+    m.kx = a.nlx / 2;
+    m.mode = (int64_t)m.ky * a.nlx + m.kx;
+    m.mirror = -1;
+    return true;
+}
 
 constexpr int kMarchThreads = 128;
 
@@ -242,11 +306,9 @@ k_march(const MarchArgs a)
     }
     __syncthreads();
 
-    const int64_t mode = (int64_t)blockIdx.x * kMarchThreads + threadIdx.x;
-    if (mode >= (int64_t)a.nlx * a.nly_loc) return;
-    const int kyl = (int)(mode / a.nlx);
-    const int kx = (int)(mode - (int64_t)kyl * a.nlx);
-    const int ky = a.ky0 + kyl;
+    ModeMap mm;
+    if (!march_map(a, (int64_t)blockIdx.x * kMarchThreads + threadIdx.x, mm)) return;
+    const int kx = mm.kx, ky = mm.ky;
     const double lx = a.lx[kx], ly = a.ly[ky];
 
     // source spectrum of this mode (solver.py:134 / :136-145)
@@ -261,7 +323,7 @@ k_march(const MarchArgs a)
         q0r = sv.x * a.src_scale; q0i = sv.y * a.src_scale;
     }
 
-    const Emit emit(a, gd, mode, lx, ly);
+    const Emit emit(a, gd, mm.mode, mm.mirror, lx, ly);
 
     if (ky == 0 && kx == 0) {
         // degenerate mode: flux constant, concentration by the trapezoid rule (solver.py:190-191,239-251)
@@ -374,11 +436,9 @@ __global__ void __launch_bounds__(kMarchThreads)
 k_analytic(const MarchArgs a)
 {
     const GroupDesc gd = a.groups[blockIdx.y];
-    const int64_t mode = (int64_t)blockIdx.x * kMarchThreads + threadIdx.x;
-    if (mode >= (int64_t)a.nlx * a.nly_loc) return;
-    const int kyl = (int)(mode / a.nlx);
-    const int kx = (int)(mode - (int64_t)kyl * a.nlx);
-    const int ky = a.ky0 + kyl;
+    ModeMap mm;
+    if (!march_map(a, (int64_t)blockIdx.x * kMarchThreads + threadIdx.x, mm)) return;
+    const int kx = mm.kx, ky = mm.ky;
     const double lx = a.lx[kx], ly = a.ly[ky];
     double q0r, q0i;
     if (a.footprint) {
@@ -390,7 +450,7 @@ k_analytic(const MarchArgs a)
         const double2 sv = a.src_spec[(size_t)(wy - a.src_ky0) * a.src_pitch + wx];
         q0r = sv.x * a.src_scale; q0i = sv.y * a.src_scale;
     }
-    const Emit emit(a, gd, mode, lx, ly);
+    const Emit emit(a, gd, mm.mode, mm.mirror, lx, ly);
     const double h = gd.h_analytic;
     if (ky == 0 && kx == 0) {
         // tfftp[:,0,0] = p000 - tfftq0[0,0]*Kzinv*h ; tfftq[:,0,0] = tfftq0[0,0]

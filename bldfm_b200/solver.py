@@ -39,6 +39,8 @@ def _flags(footprint, analytic, precision):
         f |= _lib.FFT_LIBRARY
     if config.FFT_FULL:
         f |= _lib.FFT_FULL
+    if config.MARCH_FULL:
+        f |= _lib.MARCH_FULL
     return f
 
 

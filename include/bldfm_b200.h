@@ -48,6 +48,8 @@ extern "C" {
                                          solve's kernels (double-buffered device results, separate copy stream) */
 #define BLDFM_FFT_LIBRARY      0x080  /* force the cuFFT transform path instead of the pruned in-house kernels    */
 #define BLDFM_FFT_FULL         0x100  /* in-house back-transform without the real-output (Hermitian) halving      */
+#define BLDFM_MARCH_FULL       0x200  /* march every retained mode instead of the half-plane ky <= nly/2 whose
+                                         conjugates fill the other half (cross-check; same values bit for bit)  */
 
 typedef struct bldfm_plan bldfm_plan;
 

@@ -256,3 +256,41 @@ def test_edge_geometries_against_oracle(B, oracle, shape, modes, halo, fft):
     finally:
         B.config.FFT_LIBRARY = False
         B.config.FFT_FULL = False
+
+
+@pytest.mark.parametrize("shape,modes,halo", [
+    ((32, 48), (48, 32), 0.0),        # even x even, no truncation
+    ((24, 40), (16, 8), 35.0),        # truncated modes
+    ((2, 2), (2, 2), None),           # only row 0 and the Nyquist row/column
+    ((15, 45), (512, 512), 0.0),      # clamped to odd x odd: every non-zero mode has a partner
+    ((33, 20), (512, 512), 0.0),      # odd rows, even columns
+    ((64, 64), (64, 64), None),
+])
+def test_half_plane_march_equals_full_march(B, shape, modes, halo):
+    """The default march covers rows ky <= nly/2 and stores conjugates for the rest (march.cuh);
+    BLDFM_MARCH_FULL marches every retained mode like the reference.  Footprint spectra must agree
+    BITWISE (the source spectrum is an exact constant); with a real source field the two differ only
+    by the Hermitian asymmetry of the computed source spectrum: ulp-level, amplified by the shooting
+    combine like any other round-off (5e-12 on the worst of these small grids)."""
+    from bldfm_b200.pbl_model import vertical_profiles
+    from bldfm_b200.solver import spectral_fields
+    ny, nx = shape
+    dom = (nx * 9.25, ny * 11.5)      # geometry unique to this test -> a fresh plan, no stale spectra
+    z, prof = vertical_profiles(12, 8.0, (2.5, -3.5), ustar=0.35, mol=-80.0)
+    rng = np.random.default_rng(nx * 100 + ny)
+    src = rng.random((ny, nx))
+    for footprint in (True, False):
+        for levels in ([12], [0, 7, 12]):
+            kw = dict(srf_flx=src, z=z, profiles=prof, domain=dom, levels=levels, modes=modes,
+                      meas_pt=(dom[0] * 0.4, dom[1] * 0.6), footprint=footprint, halo=halo,
+                      srf_bg_conc=0.3, precision="double")
+            hp, hq = spectral_fields(**kw)
+            B.config.MARCH_FULL = True
+            try:
+                fp, fq = spectral_fields(**kw)
+            finally:
+                B.config.MARCH_FULL = False
+            if footprint:
+                assert np.array_equal(hp, fp) and np.array_equal(hq, fq)
+            else:
+                assert rel_l2c(hp, fp) <= TOL_F64 and rel_l2c(hq, fq) <= TOL_F64
