@@ -358,17 +358,29 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     if (analytic && nlv != 1)
         return fail(BLDFM_ERR_ANALYTIC_LEVELS, "analytic=True supports a single output level.");
 
-    int ky0 = 0, rows = g.nly;
+    // half-plane march (march.cuh): rows ky0 .. ky0+rows-1 of ky <= nly/2 are marched, the spectra keep
+    // the full [nly][nlx] layout (conjugates stored at (-ky,-kx)).  BLDFM_MARCH_FULL: every row is marched.
+    const bool herm = !(flags & BLDFM_MARCH_FULL);
+    int ky0 = 0, rows = herm ? g.nly / 2 + 1 : g.nly;
+    int lay_rows = g.nly;                 // rows per field of the spectra buffers
     if (sh) {
         if (nprob != 1) return fail(BLDFM_ERR_INVALID, "sharded solve takes one problem");
         if (sh->nranks < 1 || sh->rank < 0 || sh->rank >= sh->nranks) return fail(BLDFM_ERR_INVALID, "bad rank / nranks");
-        if (g.nly % sh->nranks || g.nx % sh->nranks)
-            return fail(BLDFM_ERR_INVALID, "sharded solve needs nly and nx divisible by the number of ranks");
+        if (g.nx % sh->nranks || (!herm && g.nly % sh->nranks))
+            return fail(BLDFM_ERR_INVALID, "sharded solve needs nx (and nly with BLDFM_MARCH_FULL) divisible by the number of ranks");
         if (!pruned_fft_supported(g, false, pl->smem_optin))
             return fail(BLDFM_ERR_INVALID, "sharded solve needs the in-house transform (size factors 2,3,5; <= 227 KB shared memory)");
         if (!sh->send_p || !sh->send_q) return fail(BLDFM_ERR_INVALID, "send buffers are NULL");
-        rows = g.nly / sh->nranks;
-        ky0 = sh->rank * rows;
+        if (herm) {
+            const int Rp = herm_shard_rows(g, sh->nranks);
+            ky0 = sh->rank * Rp;
+            rows = std::min(Rp, g.nly / 2 + 1 - ky0);
+            if (rows < 1) return fail(BLDFM_ERR_INVALID, "sharded solve: more ranks than row blocks of the half-plane");
+        } else {
+            rows = g.nly / sh->nranks;
+            ky0 = sh->rank * rows;
+            lay_rows = rows;
+        }
     }
 
     DeviceGuard guard(pl->device);
@@ -512,16 +524,33 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
                                    reinterpret_cast<cufftDoubleComplex*>(d_pad), CUFFT_FORWARD));
             d_src_spec = d_pad;
         } else {
-            // pruned: [ny][nlx] intermediate + compact [nly][nlx] spectrum
+            // pruned: [ny][nlx] intermediate + compact spectrum [lay_rows][nlx]
             const size_t wbytes = sizeof(double2) * (size_t)g.ny * g.nlx;
-            const size_t sbytes = sizeof(double2) * (size_t)rows * g.nlx;
+            const size_t sbytes = sizeof(double2) * (size_t)lay_rows * g.nlx;
             TRY(pl->src_pad.ensure(wbytes + sbytes));
             char* base = static_cast<char*>(pl->src_pad.p);
             PrunedFftTables tab;
             TRY(ensure_twiddles(pl, false, &tab));
             int nl = 0;
-            cudaError_t fe = pruned_fft_forward(pl->stream, pl->smem_optin, g, d_q0, base, base + wbytes, tab, &nl,
-                                                ky0, rows);
+            cudaError_t fe;
+            if (herm && sh) {
+                // this rank's rows and -- for the modes (-ky, Nyquist kx) it marches on top -- their partner rows
+                char* spec = base + wbytes;
+                fe = pruned_fft_forward(pl->stream, pl->smem_optin, g, d_q0, base, spec + sizeof(double2) * (size_t)ky0 * g.nlx,
+                                        tab, &nl, ky0, rows);
+                int e_lo, n_extra;
+                march_extras(g.nlx, g.nly, ky0, rows, e_lo, n_extra);
+                if (fe == cudaSuccess && n_extra > 0) {
+                    const int m0 = g.nly - (e_lo + n_extra - 1);
+                    fe = pruned_fft_forward(pl->stream, pl->smem_optin, g, d_q0, base, spec + sizeof(double2) * (size_t)m0 * g.nlx,
+                                            tab, &nl, m0, n_extra, true);
+                }
+            } else if (herm) {
+                // rows 0 .. nly/2 are marched; the Nyquist-column partners need the other rows too
+                fe = pruned_fft_forward(pl->stream, pl->smem_optin, g, d_q0, base, base + wbytes, tab, &nl, 0, g.nly);
+            } else {
+                fe = pruned_fft_forward(pl->stream, pl->smem_optin, g, d_q0, base, base + wbytes, tab, &nl, ky0, rows);
+            }
             if (fe != cudaSuccess) return fail(BLDFM_ERR_CUDA, std::string("pruned forward FFT: ") + cudaGetErrorString(fe));
             pl->launches += nl;
             d_src_spec = reinterpret_cast<const double2*>(base + wbytes);
@@ -532,7 +561,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
 
     // ---- K4-K8: fused march -> compact spectra
     nvtxMarkA("bldfm:march");
-    const int64_t nmodes = (int64_t)g.nlx * rows;
+    const int64_t nmodes = (int64_t)g.nlx * lay_rows;
     const int64_t nfields = (int64_t)nprob * nlv;
     TRY(pl->spec_p.ensure((size_t)nfields * nmodes * celem));
     TRY(pl->spec_q.ensure((size_t)nfields * nmodes * celem));
@@ -545,18 +574,18 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         char* dbase = static_cast<char*>(pl->params.p);
         MarchArgs a{};
         a.nlx = g.nlx; a.nly = g.nly; a.nlv = nlv;
-        a.ky0 = ky0; a.nly_loc = rows;
+        a.ky0 = ky0; a.nrows = rows; a.nly_loc = lay_rows;
         a.coef_stride = coef_stride; a.nrow_of = nz_max;
         a.snap_level = lp.snap_level; a.last_level = lp.last_level;
         a.single = dbl ? 0 : 1;
         a.out_f32 = spec_f32 ? 1 : 0;
         a.footprint = footprint ? 1 : 0;
         // conjugate symmetry of the spectra of a real source: march half the modes (march.cuh)
-        a.herm = (!sh && !(flags & BLDFM_MARCH_FULL)) ? 1 : 0;
+        a.herm = herm ? 1 : 0;
         a.src_pitch = src_compact ? g.nlx : g.nxe;
         a.src_nfx = src_compact ? g.nlx : g.nxe;
         a.src_nfy = src_compact ? g.nly : g.nye;
-        a.src_ky0 = src_compact ? ky0 : 0;
+        a.src_ky0 = (src_compact && !herm) ? ky0 : 0;
         a.q0_const = 1.0 / g.nxe / g.nye;                           // solver.py:134
         a.src_scale = 1.0 / ((double)g.nxe * (double)g.nye);        // norm="forward"
         a.src_spec = d_src_spec;
@@ -569,7 +598,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         a.outp = pl->spec_p.p; a.outq = pl->spec_q.p;
         a.slot_stride = (int64_t)nlv * nmodes;
 
-        const int64_t nthreads = march_thread_count(g.nlx, rows, g.nly, a.herm != 0);
+        const int64_t nthreads = march_thread_count(g.nlx, g.nly, ky0, rows, herm);
         const dim3 grid((unsigned)((nthreads + kMarchThreads - 1) / kMarchThreads), (unsigned)ngroups);
         const size_t smem = (size_t)coef_stride * sizeof(LevelCoef) + (size_t)nz_max * sizeof(int32_t);
         if (smem > pl->smem_optin)
@@ -598,9 +627,12 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         PrunedFftTables tab;
         TRY(ensure_twiddles(pl, false, &tab));
         int nl = 0;
-        cudaError_t fe = sharded_xpass(pl->stream, pl->smem_optin, g, footprint, rows, sh->nranks, pl->spec_p.p,
-                                       pl->spec_q.p, (int)nfields, sh->send_p, sh->send_q, sh->peer_p, sh->peer_q,
-                                       (int64_t)g.nly * (g.nx / sh->nranks), tab, &nl);
+        cudaError_t fe = herm
+            ? herm_sharded_xpass(pl->stream, pl->smem_optin, g, footprint, ky0, rows, sh->nranks, pl->spec_p.p,
+                                 pl->spec_q.p, (int)nfields, sh->send_p, sh->send_q, sh->peer_p, sh->peer_q, tab, &nl)
+            : sharded_xpass(pl->stream, pl->smem_optin, g, footprint, rows, sh->nranks, pl->spec_p.p,
+                            pl->spec_q.p, (int)nfields, sh->send_p, sh->send_q, sh->peer_p, sh->peer_q,
+                            (int64_t)g.nly * (g.nx / sh->nranks), tab, &nl);
         if (fe != cudaSuccess) return fail(BLDFM_ERR_CUDA, std::string("sharded x-pass: ") + cudaGetErrorString(fe));
         pl->launches += nl;
         if (pl->profiling) {
@@ -1055,8 +1087,9 @@ int bldfm_sharded_stage2(bldfm_plan* pl, int32_t nlv, int flags, int32_t rank, i
     (void)rank;
     if (!pl || !recv_p || !recv_q || !conc_slab || !flx_slab) return fail(BLDFM_ERR_INVALID, "NULL argument");
     const bldfm_geometry& g = pl->g;
-    if (nranks < 1 || g.nly % nranks || g.nx % nranks)
-        return fail(BLDFM_ERR_INVALID, "sharded solve needs nly and nx divisible by the number of ranks");
+    const bool herm = !(flags & BLDFM_MARCH_FULL);
+    if (nranks < 1 || g.nx % nranks || (!herm && g.nly % nranks))
+        return fail(BLDFM_ERR_INVALID, "sharded solve needs nx (and nly with BLDFM_MARCH_FULL) divisible by the number of ranks");
     if (!pruned_fft_supported(g, false, pl->smem_optin))
         return fail(BLDFM_ERR_INVALID, "sharded solve needs the in-house transform");
     DeviceGuard guard(pl->device);
@@ -1064,8 +1097,11 @@ int bldfm_sharded_stage2(bldfm_plan* pl, int32_t nlv, int flags, int32_t rank, i
     PrunedFftTables tab;
     TRY(ensure_twiddles(pl, false, &tab));
     int nl = 0;
-    cudaError_t fe = sharded_ypass(pl->stream, pl->smem_optin, g, (flags & BLDFM_FOOTPRINT) != 0, nranks, recv_p,
-                                   recv_q, nlv, conc_slab, flx_slab, tab, &nl);
+    cudaError_t fe = herm
+        ? herm_sharded_ypass(pl->stream, pl->smem_optin, g, (flags & BLDFM_FOOTPRINT) != 0, nranks, recv_p, recv_q,
+                             nlv, conc_slab, flx_slab, tab, &nl)
+        : sharded_ypass(pl->stream, pl->smem_optin, g, (flags & BLDFM_FOOTPRINT) != 0, nranks, recv_p,
+                        recv_q, nlv, conc_slab, flx_slab, tab, &nl);
     if (fe != cudaSuccess) return fail(BLDFM_ERR_CUDA, std::string("sharded y-pass: ") + cudaGetErrorString(fe));
     pl->launches += nl;
     if (!(flags & BLDFM_ASYNC)) CUDA_TRY(cudaStreamSynchronize(pl->stream));

@@ -633,7 +633,7 @@ inline cudaError_t sharded_ypass(cudaStream_t stream, size_t smem_optin, const b
 // `work` holds [ny][nlx] c128.  Two launches.
 inline cudaError_t pruned_fft_forward(cudaStream_t stream, size_t smem_optin, const bldfm_geometry& g,
                                       const double* q0, void* work, void* spec, const PrunedFftTables& tab,
-                                      int* nlaunch, int ky0 = 0, int rows = -1)
+                                      int* nlaunch, int ky0 = 0, int rows = -1, bool skip_x = false)
 {
     if (rows < 0) rows = g.nly;      // ky-slab sharding: only rows [ky0, ky0+rows) of the spectrum
     std::vector<int> rx, ry;
@@ -663,13 +663,16 @@ inline cudaError_t pruned_fft_forward(cudaStream_t stream, size_t smem_optin, co
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_fft_pass<double, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
     if (e != cudaSuccess) return e;
-    k_fft_pass<double, true, false><<<dim3((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), 1),
-                                      fft_pick_threads(ax.N, ax.cw, ax.radix[0]),
-                                      fft_smem_bytes(ax.N, ax.cw, false), stream>>>(ax);
+    if (!skip_x) {     // `work` already holds the x-pass when a second row range of the same source is asked for
+        k_fft_pass<double, true, false><<<dim3((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), 1),
+                                          fft_pick_threads(ax.N, ax.cw, ax.radix[0]),
+                                          fft_smem_bytes(ax.N, ax.cw, false), stream>>>(ax);
+        *nlaunch += 1;
+    }
     k_fft_pass<double, false, false><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), 1),
                                        fft_pick_threads(ay.N, ay.cw, ay.radix[0]),
                                        fft_smem_bytes(ay.N, ay.cw, false), stream>>>(ay);
-    *nlaunch += 2;
+    *nlaunch += 1;
     return cudaGetLastError();
 }
 

@@ -30,6 +30,12 @@ struct FftHArgs {
     int32_t nx;                // kept columns
     int32_t out_off, n_out;    // output window of this pass
     int32_t nfields_first;
+    // ky-slab sharding (pass X): this launch transforms the rows row0 .. row0+ntrans-1 of A and blocks
+    // the kept columns by destination rank: out[field][blk][row-row0][out_block] (out_block = nx/G), or
+    // straight into the peers' receive buffers out_peer[blk][field][row-row0][out_block]
+    int32_t row0, out_block;
+    int64_t out_field_stride, out_block_stride;
+    void* const* out_peer;
     const void* in;            // pass X: S [field][nly][nlx]      pass Y: A [field][nrow][nx]
     const void* in2;
     void* out;                 // pass X: A [field][nrow][nx]      pass Y: real [field][ny][nx]
@@ -95,7 +101,16 @@ __device__ __forceinline__ void herm_emit(const FftHArgs& a, void* outp, size_t 
     const int o = i - a.out_off;
     if (o < 0 || o >= a.n_out) return;
     if (PASS == 0) {
-        reinterpret_cast<V*>(outp)[(field * a.nrow + tg) * (size_t)a.nx + o] = mk2<T>(v.r, sgn * v.i);
+        if (a.out_block > 0) {
+            const int blk = o / a.out_block;
+            const int jb = o - blk * a.out_block;
+            V* dst = reinterpret_cast<V*>(a.out_peer ? a.out_peer[blk] : outp);
+            const size_t off = field * (size_t)a.out_field_stride + (a.out_peer ? 0 : blk * (size_t)a.out_block_stride) +
+                               (size_t)(tg - a.row0) * a.out_block + jb;
+            dst[off] = mk2<T>(v.r, sgn * v.i);
+        } else {
+            reinterpret_cast<V*>(outp)[(field * a.nrow + tg) * (size_t)a.nx + o] = mk2<T>(v.r, sgn * v.i);
+        }
     } else {
         T* dst = reinterpret_cast<T*>(outp) + (field * a.n_out + o) * (size_t)a.nx + 2 * tg;
         const T im = sgn * v.i;
@@ -208,8 +223,8 @@ k_fft_h(const FftHArgs a)
     extern __shared__ __align__(16) unsigned char fft_smem[];
     V* buf = reinterpret_cast<V*>(fft_smem);
     const int N = a.N;
-    const int t0 = blockIdx.x * a.cw;
-    const int cw = min(a.cw, a.ntrans - t0);
+    const int cw = min(a.cw, a.ntrans - (int)blockIdx.x * a.cw);
+    const int t0 = blockIdx.x * a.cw + (PASS == 0 ? a.row0 : 0);
     const bool second = (int)blockIdx.y >= a.nfields_first;
     const size_t field = second ? blockIdx.y - a.nfields_first : blockIdx.y;
     const size_t in_stride = PASS == 0 ? (size_t)a.nly * a.nlx : (size_t)a.nrow * a.nx;
@@ -315,6 +330,81 @@ inline cudaError_t herm_fft_launch(cudaStream_t stream, size_t smem_optin, const
                         fft_pick_threads(ay.N, ay.cw, ay.radix[0]), sy, stream>>>(by);
         *nlaunch += 2;
     }
+    return cudaGetLastError();
+}
+
+// ---- ky-slab sharded real-output back-transform -------------------------------------
+// The nly/2+1 rows of A are split in blocks of Rp = ceil((nly/2+1)/G) rows: rank r owns rows
+// [r*Rp, min((r+1)*Rp, nly/2+1)).  Receiver layout per field: [G*Rp][nx/G] (row = global row of A).
+inline int herm_shard_rows(const bldfm_geometry& g, int nranks) { return (g.nly / 2 + 1 + nranks - 1) / nranks; }
+
+// stage 1: pass X over this rank's rows of A, output blocked by destination rank
+inline cudaError_t herm_sharded_xpass(cudaStream_t stream, size_t smem_optin, const bldfm_geometry& g,
+                                      bool forward_dir, int row0, int rows, int nranks, const void* spec_p,
+                                      const void* spec_q, int nfields, void* send_p, void* send_q,
+                                      void* const* peer_p, void* const* peer_q, const PrunedFftTables& tab,
+                                      int* nlaunch)
+{
+    std::vector<int> rx;
+    fft_factorize(g.nfx, rx);
+    const int nxl = g.nx / nranks;
+    const int Rp = herm_shard_rows(g, nranks);
+    FftHArgs ax{};
+    ax.N = g.nfx; ax.nstages = (int)rx.size();
+    { FftPassArgs tmp{}; fft_set_stages(tmp, rx); for (int i = 0; i < tmp.nstages; ++i) { ax.radix[i] = tmp.radix[i]; ax.lshift[i] = tmp.lshift[i]; } }
+    ax.cw = fft_pick_cw(g.nfx, false, smem_optin, 4, (int64_t)rows * 2 * nfields);
+    ax.ntrans = rows; ax.conj_io = forward_dir ? 0 : 1;
+    ax.nlx = g.nlx; ax.nly = g.nly; ax.nrow = g.nly / 2 + 1; ax.nx = g.nx;
+    ax.out_off = g.px; ax.n_out = g.nx;
+    ax.twiddle = tab.tw_x; ax.rev = tab.rev_x;
+    ax.row0 = row0; ax.out_block = nxl;
+    ax.out_field_stride = (int64_t)nranks * Rp * nxl;
+    ax.out_block_stride = (int64_t)Rp * nxl;
+    ax.nfields_first = nfields;
+    ax.in = spec_p; ax.in2 = spec_q; ax.out = send_p; ax.out2 = send_q;
+    cudaError_t e = cudaFuncSetAttribute(k_fft_h<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    if (e != cudaSuccess) return e;
+    const unsigned gx = (unsigned)((rows + ax.cw - 1) / ax.cw);
+    const int th = fft_pick_threads(ax.N, ax.cw, ax.radix[0]);
+    const size_t sm = fft_smem_bytes(ax.N, ax.cw, false);
+    if (peer_p) {
+        // the p fields then the q fields: each has its own table of peer pointers
+        FftHArgs a1 = ax; a1.in2 = spec_p; a1.out_peer = peer_p;
+        k_fft_h<double, 0><<<dim3(gx, (unsigned)nfields), th, sm, stream>>>(a1);
+        FftHArgs a2 = ax; a2.in = spec_q; a2.in2 = spec_q; a2.out_peer = peer_q;
+        k_fft_h<double, 0><<<dim3(gx, (unsigned)nfields), th, sm, stream>>>(a2);
+        *nlaunch += 2;
+    } else {
+        k_fft_h<double, 0><<<dim3(gx, (unsigned)(2 * nfields)), th, sm, stream>>>(ax);
+        *nlaunch += 1;
+    }
+    return cudaGetLastError();
+}
+
+// stage 2: pass Y (column pairs) over the received [field][G*Rp][nx/G] -> real [field][ny][nx/G]
+inline cudaError_t herm_sharded_ypass(cudaStream_t stream, size_t smem_optin, const bldfm_geometry& g,
+                                      bool forward_dir, int nranks, const void* recv_p, const void* recv_q,
+                                      int nfields, void* out_p, void* out_q, const PrunedFftTables& tab, int* nlaunch)
+{
+    std::vector<int> ry;
+    fft_factorize(g.nfy, ry);
+    const int nxl = g.nx / nranks;
+    FftHArgs ay{};
+    ay.N = g.nfy; ay.nstages = (int)ry.size();
+    { FftPassArgs tmp{}; fft_set_stages(tmp, ry); for (int i = 0; i < tmp.nstages; ++i) { ay.radix[i] = tmp.radix[i]; ay.lshift[i] = tmp.lshift[i]; } }
+    ay.ntrans = (nxl + 1) / 2;
+    ay.cw = fft_pick_cw(g.nfy, false, smem_optin, 4, (int64_t)ay.ntrans * 2 * nfields);
+    ay.conj_io = forward_dir ? 0 : 1;
+    ay.nlx = g.nlx; ay.nly = g.nly; ay.nrow = nranks * herm_shard_rows(g, nranks); ay.nx = nxl;
+    ay.out_off = g.py; ay.n_out = g.ny;
+    ay.twiddle = tab.tw_y; ay.rev = tab.rev_y;
+    ay.nfields_first = nfields;
+    ay.in = recv_p; ay.in2 = recv_q; ay.out = out_p; ay.out2 = out_q;
+    cudaError_t e = cudaFuncSetAttribute(k_fft_h<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    if (e != cudaSuccess) return e;
+    k_fft_h<double, 1><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), (unsigned)(2 * nfields)),
+                         fft_pick_threads(ay.N, ay.cw, ay.radix[0]), fft_smem_bytes(ay.N, ay.cw, false), stream>>>(ay);
+    *nlaunch += 1;
     return cudaGetLastError();
 }
 

@@ -99,10 +99,11 @@ __device__ __forceinline__ void propagator(const LevelCoef& c, double lx, double
         P.br = c.c0 - (c.s6 * tr) * c.h3;
         P.bi = -((c.s6 * ti) * c.h3);
         const double t2r = tr * tr - ti * ti;
-        const double m = tr * ti;
-        const double t2i = m + m;                  // == tr*ti + ti*tr bitwise
+        const double m = tr * ti;                  // t2i = tr*ti + ti*tr == 2m exactly
         P.cr = tr * c.h - (c.s61 * t2r) * c.h3;
-        P.ci = ti * c.h - (c.s61 * t2i) * c.h3;
+        // (s61*(2m))*h3 == 2*((s61*m)*h3) exactly (scaling by 2 commutes with rounding), and
+        // fma(-2, x, y) rounds y - 2x once, like the reference's subtraction: one DADD saved
+        P.ci = fma(-2.0, (c.s61 * m) * c.h3, ti * c.h);
     } else {
         const double tr = -fma(c.Kx, lx2, c.Ky * ly2);
         const double ti = -fma(c.u, lx, c.v * ly);
@@ -141,7 +142,8 @@ __device__ __forceinline__ void apply(const Prop& P, double& pr, double& pi, dou
 // ------------------------------------------------------------------------------------------------
 struct MarchArgs {
     int32_t nlx, nly;          // retained modes
-    int32_t ky0, nly_loc;      // this launch covers rows ky0 .. ky0+nly_loc-1 (ky-slab sharding)
+    int32_t ky0, nrows;        // this launch marches rows ky0 .. ky0+nrows-1 (ky-slab sharding)
+    int32_t nly_loc;           // rows per field of the output spectra (nrows; nly in half-plane mode)
     int32_t nlv;               // output rows
     int32_t coef_stride;       // LevelCoef entries per group (= max steps)
     int32_t nrow_of;           // entries in row_of (= max nz)
@@ -150,7 +152,7 @@ struct MarchArgs {
     int32_t single;            // precision == "single": round tfftp/tfftq to complex64 values
     int32_t out_f32;           // spectra stored as float2 (no shift applied, single)
     int32_t footprint;
-    int32_t herm;              // 1: march only the half-plane ky <= nly/2 and store the conjugate mirror
+    int32_t herm;              // 1: rows lie in the half-plane ky <= nly/2; conjugates are stored at (-ky,-kx)
     int32_t src_pitch;         // row pitch (complex elements) of src_spec
     int32_t src_nfx, src_nfy;  // size of the forward spectrum for index wrapping
     int32_t src_ky0;           // first ky row held by src_spec (ky-slab sharding), else 0
@@ -243,20 +245,32 @@ struct Emit {
 // the conjugate at (-ky,-kx).  Modes without a partner in the retained set are marched on their own:
 // row 0 (its partner is in the same row; marched in full), the Nyquist row ky = nly/2 and the Nyquist
 // column kx = nlx/2 (even sizes; fftfreq keeps only -n/2) -- the latter's lower half by extra threads
-// appended after the half-plane.
+// appended after the rows of the launch.
 struct ModeMap { int ky, kx; int64_t mode, mirror; };
 
-__host__ __device__ __forceinline__ int64_t march_thread_count(int nlx, int nly_loc, int nly, bool herm)
+// extra threads of a half-plane launch over rows [row0, row0+rows): the modes (-ky, Nyquist kx) of the
+// rows ky in [e_lo, e_lo+n_extra) that have a partner row
+__host__ __device__ __forceinline__ void march_extras(int nlx, int nly, int row0, int rows, int& e_lo, int& n_extra)
 {
-    if (!herm) return (int64_t)nlx * nly_loc;
     const int nmir = (nly - 1) / 2;                        // rows 1..nmir have a partner row nly-ky
-    return (int64_t)nlx * (nly / 2 + 1) + ((nlx % 2 == 0) ? nmir : 0);
+    e_lo = row0 > 1 ? row0 : 1;
+    const int e_hi = (row0 + rows) < (nmir + 1) ? (row0 + rows) : (nmir + 1);
+    n_extra = (nlx % 2 == 0 && e_hi > e_lo) ? e_hi - e_lo : 0;
+}
+
+__host__ __device__ __forceinline__ int64_t march_thread_count(int nlx, int nly, int row0, int rows, bool herm)
+{
+    int e_lo, n_extra = 0;
+    if (herm) march_extras(nlx, nly, row0, rows, e_lo, n_extra);
+    return (int64_t)nlx * rows + n_extra;
 }
 
 __device__ __forceinline__ bool march_map(const MarchArgs& a, int64_t tid, ModeMap& m)
 {
+    const int64_t nmain = (int64_t)a.nlx * a.nrows;
     if (!a.herm) {
-        if (tid >= (int64_t)a.nlx * a.nly_loc) return false;
+        // spectra hold the rows ky0 .. ky0+nrows-1 only
+        if (tid >= nmain) return false;
         const int kyl = (int)(tid / a.nlx);
         m.kx = (int)(tid - (int64_t)kyl * a.nlx);
         m.ky = a.ky0 + kyl;
@@ -264,21 +278,23 @@ __device__ __forceinline__ bool march_map(const MarchArgs& a, int64_t tid, ModeM
         m.mirror = -1;
         return true;
     }
-    const int nrow = a.nly / 2 + 1;
+    // spectra hold all nly rows; this launch fills rows ky0 .. ky0+nrows-1 (<= nly/2) and their mirrors
     const int nmir = (a.nly - 1) / 2;
     const bool even_x = (a.nlx % 2) == 0;
-    const int64_t nmain = (int64_t)a.nlx * nrow;
     if (tid < nmain) {
-        m.ky = (int)(tid / a.nlx);
-        m.kx = (int)(tid - (int64_t)m.ky * a.nlx);
-        m.mode = tid;
+        const int kyl = (int)(tid / a.nlx);
+        m.kx = (int)(tid - (int64_t)kyl * a.nlx);
+        m.ky = a.ky0 + kyl;
+        m.mode = (int64_t)m.ky * a.nlx + m.kx;
         const bool has = m.ky >= 1 && m.ky <= nmir && !(even_x && m.kx == a.nlx / 2);
         m.mirror = has ? (int64_t)(a.nly - m.ky) * a.nlx + (m.kx == 0 ? 0 : a.nlx - m.kx) : -1;
         return true;
     }
+    int e_lo, n_extra;
+    march_extras(a.nlx, a.nly, a.ky0, a.nrows, e_lo, n_extra);
     const int64_t e = tid - nmain;
-    if (!even_x || e >= nmir) return false;
-    m.ky = nrow + (int)e;
+    if (e >= n_extra) return false;
+    m.ky = a.nly - (e_lo + (int)e);
     m.kx = a.nlx / 2;
     m.mode = (int64_t)m.ky * a.nlx + m.kx;
     m.mirror = -1;
@@ -356,7 +372,7 @@ k_march(const MarchArgs a)
     if (!MULTI) {
         const int snap = a.snap_level;
         const int n1 = (snap >= 0 && snap <= S) ? snap : S;
-#pragma unroll 2
+#pragma unroll 4
         for (int i = 0; i < n1; ++i) {
             propagator<FMA>(sc[i], lx, ly, lx2, ly2, P);
             apply<FMA>(P, p1r, p1i, q1r, q1i);
@@ -366,14 +382,14 @@ k_march(const MarchArgs a)
             s1pr = p1r; s1pi = p1i; s1qr = q1r; s1qi = q1i;
             s2pr = p2r; s2pi = p2i; s2qr = q2r; s2qi = q2i;
         }
-#pragma unroll 2
+#pragma unroll 4
         for (int i = n1; i < S; ++i) {
             propagator<FMA>(sc[i], lx, ly, lx2, ly2, P);
             apply<FMA>(P, p1r, p1i, q1r, q1i);
             apply<FMA>(P, p2r, p2i, q2r, q2i);
         }
     } else {
-#pragma unroll 2
+#pragma unroll 4
         for (int i = 0; i < S; ++i) {
             propagator<FMA>(sc[i], lx, ly, lx2, ly2, P);
             apply<FMA>(P, p1r, p1i, q1r, q1i);

@@ -3,13 +3,18 @@
 Every rank (one process per GPU, ``torch.distributed`` initialised with NCCL) calls
 ``steady_state_transport_solver_sharded`` with the SAME arguments.  Rank r
 
-  1. marches the retained Fourier rows ``ky in [r*nly/G, (r+1)*nly/G)`` (modes are independent) and
-     x-transforms them (``bldfm_sharded_stage1``);
+  1. marches its block of the half-plane rows ``ky in [0, nly/2]`` (modes are independent, and the spectra
+     of a real source are conjugate-symmetric, so the other half-plane is never marched) and x-transforms
+     them (``bldfm_sharded_stage1``).  Blocks hold ``Rp = ceil((nly/2+1)/G)`` rows;
   2. exchanges column blocks with all peers -- the ONLY collective of the solve: either an
      ``all_to_all_single`` per field over NCCL/NVLink, or (``fused=True``) no collective at all: the
      x-transform kernel stores its output straight into the peers' receive buffers through CUDA-IPC
      mapped pointers, so the transpose rides on the kernel's own stores;
-  3. y-transforms its ``nx/G`` columns into real slabs (``bldfm_sharded_stage2``).
+  3. y-transforms its ``nx/G`` columns into real slabs (``bldfm_sharded_stage2``; real-output pass, two
+     columns per complex transform).
+
+``config.MARCH_FULL`` selects the cross-check variant instead: every retained row is marched
+(``nly/G`` rows per rank) and both passes are full complex transforms.
 
 The slabs are optionally all-gathered into the full fields.  float64.  In non-footprint mode every rank
 holds the whole source and computes only its own rows of the source spectrum (the x-pass over the ny
@@ -114,9 +119,14 @@ def steady_state_transport_solver_sharded(srf_flx, z, profiles, domain, levels, 
     srcp = None if src is None else _lib.ptr(src)
     lv, lv64 = _levels_array(levels)
     nlv = len(lv64)
-    if geom.nly % G or nx % G:
-        raise ValueError("sharded solve needs nly and nx divisible by the number of ranks")
-    rows, nxl = geom.nly // G, nx // G
+    herm = not config.MARCH_FULL
+    if nx % G or (not herm and geom.nly % G):
+        raise ValueError("sharded solve needs nx (and nly with MARCH_FULL) divisible by the number of ranks")
+    nxl = nx // G
+    # rows of one rank's block in the exchange; the receiver sees [G*rows][nx/G] per field
+    rows = -(-(geom.nly // 2 + 1) // G) if herm else geom.nly // G
+    if herm and rank * rows >= geom.nly // 2 + 1:
+        raise ValueError("sharded solve: more ranks than row blocks of the half-plane")
     L = _lib.lib()
     plan = get_fft_manager().plan(geom, dev_index)
     stream = torch.cuda.ExternalStream(L.bldfm_plan_stream(plan), device=device)
@@ -124,7 +134,7 @@ def steady_state_transport_solver_sharded(srf_flx, z, profiles, domain, levels, 
     lvp = lv64.ctypes.data_as(C.POINTER(C.c_int64))
 
     out = torch.empty((2, nlv, ny, nxl), dtype=torch.float64, device=device)
-    field_elems = nlv * geom.nly * nxl            # complex elements of one of p / q on the receiver
+    field_elems = nlv * G * rows * nxl            # complex elements of one of p / q on the receiver
 
     with torch.cuda.stream(stream):
         if fused and G > 1:

@@ -153,13 +153,17 @@ int  bldfm_solve_batched_measure(bldfm_plan *plan, int32_t nprob, const bldfm_pr
  * beyond one device.  float64.  In non-footprint mode every rank holds the whole source srf_flx and computes only
  * its own rows of the source spectrum (the x-pass over the ny source rows is replicated -- ~1 % of the march --
  * so the forward side needs no exchange).  Every rank calls
- *   stage1: march + x-transform of the retained rows [rank*nly/G, (rank+1)*nly/G); results go to the
- *           device buffers send_p/send_q laid out [nlv][dst][nly/G][nx/G] complex128, ready for an
- *           all-to-all (done by the caller, e.g. torch.distributed over NCCL) -- or, when peer_p/peer_q
- *           (DEVICE arrays of G pointers into every rank's receive buffer, offset to this rank's row
- *           block) are given, straight into the peers' memory over NVLink (fused transpose);
- *   stage2: y-transform of the received [nlv][nly][nx/G] complex128 into the real column slabs
- *           conc_slab/flx_slab [nlv][ny][nx/G] float64 (device).
+ *   stage1: march + x-transform of this rank's block of the half-plane rows ky in [0, nly/2] (the
+ *           spectra of a real source are conjugate-symmetric; blocks of Rp = ceil((nly/2+1)/G) rows,
+ *           rank r owns [r*Rp, min((r+1)*Rp, nly/2+1))); results go to the device buffers send_p/send_q
+ *           laid out [nlv][dst][Rp][nx/G] complex128, ready for an all-to-all (done by the caller, e.g.
+ *           torch.distributed over NCCL) -- or, when peer_p/peer_q (DEVICE arrays of G pointers into
+ *           every rank's receive buffer, offset to this rank's row block) are given, straight into the
+ *           peers' memory over NVLink (fused transpose);
+ *   stage2: real-output y-transform of the received [nlv][G*Rp][nx/G] complex128 into the real column
+ *           slabs conc_slab/flx_slab [nlv][ny][nx/G] float64 (device).
+ * With BLDFM_MARCH_FULL (cross-check) every retained row is marched: blocks of nly/G rows, buffers
+ * [nlv][dst][nly/G][nx/G] and [nlv][nly][nx/G], full complex transforms.
  * Both stages are enqueued on the plan's stream; BLDFM_ASYNC skips the final synchronisation. */
 int  bldfm_sharded_stage1(bldfm_plan *plan, const bldfm_problem *prob, const int64_t *levels, int32_t nlv,
                           const double *srf_flx, int flags, int32_t rank, int32_t nranks, void *send_p, void *send_q,

@@ -22,33 +22,36 @@ def _problem(n=96, nz=16, footprint=True):
                 meas_pt=(n * 3.9, n * 3.1), footprint=footprint, precision="double")
 
 
-def test_sharded_world1_equals_plain(gpu_lib):
+def _plain_and_sharded(kw, full, **skw):
+    """(plain result, sharded result) in the default half-plane / real-output mode, or -- full=True --
+    in the cross-check mode (every row marched, full complex passes)."""
     import bldfm_b200
     from bldfm_b200.sharded import steady_state_transport_solver_sharded
-    kw = _problem()
-    # the sharded passes are the full complex ones: bitwise equal to the plain solver in that mode,
-    # and equal to round-off to the default real-output (Hermitian) passes
-    bldfm_b200.config.FFT_FULL = True
+    bldfm_b200.config.FFT_FULL = full
+    bldfm_b200.config.MARCH_FULL = full
     try:
-        g0, c0, f0 = bldfm_b200.steady_state_transport_solver(**kw)
+        plain = bldfm_b200.steady_state_transport_solver(**kw)
+        shard = steady_state_transport_solver_sharded(**skw, **kw)
     finally:
         bldfm_b200.config.FFT_FULL = False
-    g1, c1, f1 = steady_state_transport_solver_sharded(**kw)
-    assert np.array_equal(c0, c1) and np.array_equal(f0, f1)
-    _, c2, f2 = bldfm_b200.steady_state_transport_solver(**kw)
-    assert np.abs(c2 - c1).max() <= 1e-13 * np.abs(c1).max()
-    assert np.abs(f2 - f1).max() <= 1e-13 * np.abs(f1).max()
-    for a, b in zip(g0, g1):
-        assert np.array_equal(a, b)
-    # non-footprint: the rank computes its rows of the source spectrum itself
-    kw = _problem(footprint=False)
-    bldfm_b200.config.FFT_FULL = True
-    try:
-        _, c0, f0 = bldfm_b200.steady_state_transport_solver(**kw)
-    finally:
-        bldfm_b200.config.FFT_FULL = False
-    _, c1, f1 = steady_state_transport_solver_sharded(**kw)
-    assert np.array_equal(c0, c1) and np.array_equal(f0, f1)
+        bldfm_b200.config.MARCH_FULL = False
+    return plain, shard
+
+
+def test_sharded_world1_equals_plain(gpu_lib):
+    import bldfm_b200
+    for footprint in (True, False):
+        kw = _problem(footprint=footprint)
+        # same kernels, same arithmetic per transform: bitwise equal to the plain solver in either mode
+        for full in (False, True):
+            (g0, c0, f0), (g1, c1, f1) = _plain_and_sharded(kw, full)
+            assert np.array_equal(c0, c1) and np.array_equal(f0, f1), (footprint, full)
+            for a, b in zip(g0, g1):
+                assert np.array_equal(a, b)
+        # and the two modes agree to round-off
+        _, c2, f2 = bldfm_b200.steady_state_transport_solver(**kw)
+        assert np.abs(c2 - c1).max() <= 1e-12 * np.abs(c1).max()
+        assert np.abs(f2 - f1).max() <= 1e-12 * np.abs(f1).max()
 
 
 def _free_port():
@@ -70,23 +73,22 @@ def _worker(rank, world, port, q):
         from bldfm_b200.sharded import release_peer_buffers, steady_state_transport_solver_sharded
         bldfm_b200.config.DEVICE = rank
         res = {}
-        kwn = _problem(footprint=False)
-        bldfm_b200.config.FFT_FULL = True
-        _, c0, f0 = bldfm_b200.steady_state_transport_solver(**kwn)
-        bldfm_b200.config.FFT_FULL = False
-        _, c1, f1 = steady_state_transport_solver_sharded(**kwn)
-        res["non-footprint"] = bool(np.array_equal(c0, c1) and np.array_equal(f0, f1))
-        kw = _problem()
-        bldfm_b200.config.FFT_FULL = True
-        _, c0, f0 = bldfm_b200.steady_state_transport_solver(**kw)
-        bldfm_b200.config.FFT_FULL = False
-        for fused in (False, True):
-            for rep in range(2):
-                _, c1, f1 = steady_state_transport_solver_sharded(fused=fused, **kw)
-            res[f"fused={fused}"] = bool(np.array_equal(c0, c1) and np.array_equal(f0, f1))
-            _, cs, fs = steady_state_transport_solver_sharded(fused=fused, gather=False, **kw)
-            nxl = c0.shape[-1] // world
-            res[f"slab fused={fused}"] = bool(np.array_equal(cs, c0[..., rank * nxl:(rank + 1) * nxl]))
+        for full in (False, True):
+            (_, c0, f0), (_, c1, f1) = _plain_and_sharded(_problem(footprint=False), full)
+            res[f"non-footprint full={full}"] = bool(np.array_equal(c0, c1) and np.array_equal(f0, f1))
+            kw = _problem()
+            for fused in (False, True):
+                for rep in range(2):
+                    (_, c0, f0), (_, c1, f1) = _plain_and_sharded(kw, full, fused=fused)
+                res[f"full={full} fused={fused}"] = bool(np.array_equal(c0, c1) and np.array_equal(f0, f1))
+                _, (_, cs, fs) = _plain_and_sharded(kw, full, fused=fused, gather=False)
+                nxl = c0.shape[-1] // world
+                res[f"slab full={full} fused={fused}"] = bool(np.array_equal(cs, c0[..., rank * nxl:(rank + 1) * nxl]))
+        # uneven blocks: 66 modes -> 34 half-plane rows -> blocks of 17; 50 -> 26 rows
+        kw = _problem(n=100)
+        kw["modes"] = (50, 66)
+        (_, c0, f0), (_, c1, f1) = _plain_and_sharded(kw, False)
+        res["truncated modes"] = bool(np.array_equal(c0, c1) and np.array_equal(f0, f1))
         release_peer_buffers()
         q.put((rank, res))
     finally:
