@@ -22,6 +22,7 @@
 #include "transform.cuh"
 #include "fft.cuh"
 #include "fft_herm.cuh"
+#include "fft24.cuh"
 
 using namespace bldfm;
 
@@ -112,6 +113,8 @@ struct bldfm_plan {
     DevBuf src_in, src_pad;  // non-footprint: device copy of srf_flx, padded complex / spectrum
     DevBuf fft_work;         // pruned path: intermediate [field][nly][nx]
     DevBuf tw64, tw32;       // pruned path: twiddle tables  x[nfx] | y[nfy]  (double2 / float2)
+    DevBuf t24_64, t24_32;   // fft24.cuh tables  x | y  (only for N = 3P passes)
+    size_t t24_off_y[2] = {0, 0};
     DevBuf out_c, out_f;     // device outputs when the caller wants host results (set 0)
     DevBuf out_c2, out_f2;   // second set: D2H of one solve overlaps the compute of the next
     int out_set = 0;
@@ -317,6 +320,27 @@ int ensure_twiddles(bldfm_plan* pl, bool f32, PrunedFftTables* tab)
     tab->tw_y = static_cast<const char*>(buf.p) + (size_t)g.nfx * esz;
     tab->rev_x = reinterpret_cast<const int32_t*>(static_cast<const char*>(buf.p) + tw_bytes);
     tab->rev_y = tab->rev_x + g.nfx;
+    // lane-contiguous tables of the specialised N = 3P passes
+    const int lqx = fft24_lq(g.nfx, g.nlx, g.nx, g.px), lqy = fft24_lq(g.nfy, g.nly, g.ny, g.py);
+    if (lqx >= 0 || lqy >= 0) {
+        DevBuf& b24 = f32 ? pl->t24_32 : pl->t24_64;
+        if (!b24.p) {
+            std::vector<double> tx, ty;
+            if (lqx >= 0) fft24_tables(lqx, tx);
+            if (lqy >= 0) fft24_tables(lqy, ty);
+            pl->t24_off_y[f32 ? 1 : 0] = tx.size() / 2 * esz;
+            tx.insert(tx.end(), ty.begin(), ty.end());
+            TRY(b24.ensure(tx.size() / 2 * esz));
+            if (f32) {
+                std::vector<float> tf(tx.begin(), tx.end());
+                CUDA_TRY(cudaMemcpy(b24.p, tf.data(), tf.size() * sizeof(float), cudaMemcpyHostToDevice));
+            } else {
+                CUDA_TRY(cudaMemcpy(b24.p, tx.data(), tx.size() * sizeof(double), cudaMemcpyHostToDevice));
+            }
+        }
+        if (lqx >= 0) tab->t24_x = b24.p;
+        if (lqy >= 0) tab->t24_y = static_cast<const char*>(b24.p) + pl->t24_off_y[f32 ? 1 : 0];
+    }
     return BLDFM_OK;
 }
 
@@ -741,9 +765,9 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
             TRY(pl->fft_work.ensure(herm_work_bytes(g, spec_f32, nfields)));
             fe = spec_f32
                 ? herm_fft_launch<float>(pl->stream, pl->smem_optin, g, forward_dir, pl->spec_p.p, pl->spec_q.p,
-                                         nfields, pl->fft_work.p, d_conc, d_flx, tab, &nl)
+                                         nfields, pl->fft_work.p, d_conc, d_flx, tab, &nl, herm)
                 : herm_fft_launch<double>(pl->stream, pl->smem_optin, g, forward_dir, pl->spec_p.p, pl->spec_q.p,
-                                          nfields, pl->fft_work.p, d_conc, d_flx, tab, &nl);
+                                          nfields, pl->fft_work.p, d_conc, d_flx, tab, &nl, herm);
         }
         if (fe != cudaSuccess) return fail(BLDFM_ERR_CUDA, std::string("pruned FFT launch: ") + cudaGetErrorString(fe));
         pl->launches += nl;
@@ -930,7 +954,7 @@ int bldfm_plan_destroy(bldfm_plan* pl)
     pl->tables.release(); pl->params.release(); pl->spec_p.release(); pl->spec_q.release();
     pl->pad_in.release(); pl->pad_out.release(); pl->src_in.release(); pl->src_pad.release();
     pl->weight.release(); pl->partial.release();
-    pl->fft_work.release(); pl->tw64.release(); pl->tw32.release(); pl->out_c.release(); pl->out_f.release();
+    pl->fft_work.release(); pl->tw64.release(); pl->tw32.release(); pl->t24_64.release(); pl->t24_32.release(); pl->out_c.release(); pl->out_f.release();
     for (auto& s : pl->staging) {
         if (s.host) cudaFreeHost(s.host);
         if (s.done) cudaEventDestroy(s.done);

@@ -485,6 +485,8 @@ struct PrunedFftTables {
     const void* tw_y = nullptr;
     const int32_t* rev_x = nullptr;
     const int32_t* rev_y = nullptr;
+    const void* t24_x = nullptr;  // lane-contiguous twiddle tables of the N = 3P passes (fft24.cuh), or NULL
+    const void* t24_y = nullptr;
 };
 
 // Runs both passes for the `nfields` compact spectra of spec_p (-> out_p) and of spec_q (-> out_q)

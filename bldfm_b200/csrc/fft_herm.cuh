@@ -30,6 +30,7 @@ struct FftHArgs {
     int32_t nx;                // kept columns
     int32_t out_off, n_out;    // output window of this pass
     int32_t nfields_first;
+    int32_t hs;                // pass X: S is conjugate-symmetric (half-plane march); used by fft24.cuh
     // ky-slab sharding (pass X): this launch transforms the rows row0 .. row0+ntrans-1 of A and blocks
     // the kept columns by destination rank: out[field][blk][row-row0][out_block] (out_block = nx/G), or
     // straight into the peers' receive buffers out_peer[blk][field][row-row0][out_block]
@@ -42,6 +43,7 @@ struct FftHArgs {
     void* out2;
     const void* twiddle;
     const int32_t* rev;
+    const void* tw24;          // fft24.cuh: [24][Q] stage-1 table | [Q] | [Q/r0] in-place stage tables
 };
 
 // S[fy][fx] with zero outside the retained set (signed frequencies)
@@ -276,11 +278,33 @@ inline size_t herm_work_bytes(const bldfm_geometry& g, bool f32, int64_t nfields
     return (size_t)2 * (size_t)chunk * (size_t)(g.nly / 2 + 1) * (size_t)g.nx * (f32 ? sizeof(float2) : sizeof(double2));
 }
 
+// specialised passes for N = 3P (fft24.cuh)
+inline int fft24_lq(int N, int nl, int n, int p);
+inline int fft24_pick_cw(int lq, bool f32, size_t smem_optin, int want, int64_t ntrans_total, int num_sms);
+template <typename T, int PASS>
+inline cudaError_t fft24_launch_pass(cudaStream_t stream, size_t smem_optin, int lq, const FftHArgs& a, dim3 grid);
+
+// launch one pass with the specialised kernel when its geometry allows (lq >= 0), else with k_fft_h
+template <typename T, int PASS>
+inline cudaError_t herm_launch_pass(cudaStream_t stream, size_t smem_optin, int lq, FftHArgs a, unsigned nfields_y,
+                                    int64_t ntrans_total)
+{
+    const bool f32 = sizeof(T) == 4;
+    if (lq >= 0 && a.tw24) {
+        a.cw = fft24_pick_cw(lq, f32, smem_optin, PASS == 1 ? 4 : 2, ntrans_total, 148);
+        return fft24_launch_pass<T, PASS>(stream, smem_optin, lq, a, dim3((unsigned)((a.ntrans + a.cw - 1) / a.cw), nfields_y));
+    }
+    k_fft_h<T, PASS><<<dim3((unsigned)((a.ntrans + a.cw - 1) / a.cw), nfields_y), fft_pick_threads(a.N, a.cw, a.radix[0]),
+                       fft_smem_bytes(a.N, a.cw, f32), stream>>>(a);
+    return cudaGetLastError();
+}
+
 // both passes for the nfields spectra of spec_p (-> out_p) and spec_q (-> out_q): two launches
 template <typename T>
 inline cudaError_t herm_fft_launch(cudaStream_t stream, size_t smem_optin, const bldfm_geometry& g,
                                    bool forward_dir, const void* spec_p, const void* spec_q, int64_t nfields,
-                                   void* work, void* out_p, void* out_q, const PrunedFftTables& tab, int* nlaunch)
+                                   void* work, void* out_p, void* out_q, const PrunedFftTables& tab, int* nlaunch,
+                                   bool herm_spec = false)
 {
     using V = typename Vec2<T>::type;
     const bool f32 = sizeof(T) == 4;
@@ -296,7 +320,11 @@ inline cudaError_t herm_fft_launch(cudaStream_t stream, size_t smem_optin, const
     ax.ntrans = nrow; ax.conj_io = forward_dir ? 0 : 1;
     ax.nlx = g.nlx; ax.nly = g.nly; ax.nrow = nrow; ax.nx = g.nx;
     ax.out_off = g.px; ax.n_out = g.nx;
-    ax.twiddle = tab.tw_x; ax.rev = tab.rev_x;
+    ax.twiddle = tab.tw_x; ax.rev = tab.rev_x; ax.tw24 = tab.t24_x;
+    ax.hs = herm_spec ? 1 : 0;
+    const bool use24 = fft_env_int("BLDFM_B200_FFT24", 1) != 0;
+    const int lqx = use24 ? fft24_lq(g.nfx, g.nlx, g.nx, g.px) : -1;
+    const int lqy = use24 ? fft24_lq(g.nfy, g.nly, g.ny, g.py) : -1;
 
     FftHArgs ay = ax;
     ay.N = g.nfy; ay.nstages = (int)ry.size();
@@ -304,14 +332,13 @@ inline cudaError_t herm_fft_launch(cudaStream_t stream, size_t smem_optin, const
     ay.cw = fft_pick_cw(g.nfy, f32, smem_optin, 4, (int64_t)((g.nx + 1) / 2) * 2 * nfields);
     ay.ntrans = (g.nx + 1) / 2;
     ay.out_off = g.py; ay.n_out = g.ny;
-    ay.twiddle = tab.tw_y; ay.rev = tab.rev_y;
+    ay.twiddle = tab.tw_y; ay.rev = tab.rev_y; ay.tw24 = tab.t24_y;
 
     cudaError_t e;
     e = cudaFuncSetAttribute(k_fft_h<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_fft_h<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
     if (e != cudaSuccess) return e;
-    const size_t sx = fft_smem_bytes(ax.N, ax.cw, f32), sy = fft_smem_bytes(ay.N, ay.cw, f32);
     const int64_t chunk = 16384;
     for (int64_t f0 = 0; f0 < nfields; f0 += chunk) {
         const int nf = (int)std::min<int64_t>(chunk, nfields - f0);
@@ -324,10 +351,10 @@ inline cudaError_t herm_fft_launch(cudaStream_t stream, size_t smem_optin, const
         by.in = bx.out; by.in2 = bx.out2;
         by.out = reinterpret_cast<T*>(out_p) + (size_t)f0 * g.ny * g.nx;
         by.out2 = reinterpret_cast<T*>(out_q) + (size_t)f0 * g.ny * g.nx;
-        k_fft_h<T, 0><<<dim3((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), (unsigned)(2 * nf)),
-                        fft_pick_threads(ax.N, ax.cw, ax.radix[0]), sx, stream>>>(bx);
-        k_fft_h<T, 1><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), (unsigned)(2 * nf)),
-                        fft_pick_threads(ay.N, ay.cw, ay.radix[0]), sy, stream>>>(by);
+        e = herm_launch_pass<T, 0>(stream, smem_optin, lqx, bx, (unsigned)(2 * nf), (int64_t)ax.ntrans * 2 * nf);
+        if (e != cudaSuccess) return e;
+        e = herm_launch_pass<T, 1>(stream, smem_optin, lqy, by, (unsigned)(2 * nf), (int64_t)ay.ntrans * 2 * nf);
+        if (e != cudaSuccess) return e;
         *nlaunch += 2;
     }
     return cudaGetLastError();
@@ -356,7 +383,7 @@ inline cudaError_t herm_sharded_xpass(cudaStream_t stream, size_t smem_optin, co
     ax.ntrans = rows; ax.conj_io = forward_dir ? 0 : 1;
     ax.nlx = g.nlx; ax.nly = g.nly; ax.nrow = g.nly / 2 + 1; ax.nx = g.nx;
     ax.out_off = g.px; ax.n_out = g.nx;
-    ax.twiddle = tab.tw_x; ax.rev = tab.rev_x;
+    ax.twiddle = tab.tw_x; ax.rev = tab.rev_x; ax.tw24 = tab.t24_x;
     ax.row0 = row0; ax.out_block = nxl;
     ax.out_field_stride = (int64_t)nranks * Rp * nxl;
     ax.out_block_stride = (int64_t)Rp * nxl;
@@ -364,18 +391,20 @@ inline cudaError_t herm_sharded_xpass(cudaStream_t stream, size_t smem_optin, co
     ax.in = spec_p; ax.in2 = spec_q; ax.out = send_p; ax.out2 = send_q;
     cudaError_t e = cudaFuncSetAttribute(k_fft_h<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
     if (e != cudaSuccess) return e;
-    const unsigned gx = (unsigned)((rows + ax.cw - 1) / ax.cw);
-    const int th = fft_pick_threads(ax.N, ax.cw, ax.radix[0]);
-    const size_t sm = fft_smem_bytes(ax.N, ax.cw, false);
+    ax.hs = 1;                                             // the sharded march is always the half-plane one
+    const int lqx = fft_env_int("BLDFM_B200_FFT24", 1) ? fft24_lq(g.nfx, g.nlx, g.nx, g.px) : -1;
     if (peer_p) {
         // the p fields then the q fields: each has its own table of peer pointers
         FftHArgs a1 = ax; a1.in2 = spec_p; a1.out_peer = peer_p;
-        k_fft_h<double, 0><<<dim3(gx, (unsigned)nfields), th, sm, stream>>>(a1);
+        e = herm_launch_pass<double, 0>(stream, smem_optin, lqx, a1, (unsigned)nfields, (int64_t)rows * nfields);
+        if (e != cudaSuccess) return e;
         FftHArgs a2 = ax; a2.in = spec_q; a2.in2 = spec_q; a2.out_peer = peer_q;
-        k_fft_h<double, 0><<<dim3(gx, (unsigned)nfields), th, sm, stream>>>(a2);
+        e = herm_launch_pass<double, 0>(stream, smem_optin, lqx, a2, (unsigned)nfields, (int64_t)rows * nfields);
+        if (e != cudaSuccess) return e;
         *nlaunch += 2;
     } else {
-        k_fft_h<double, 0><<<dim3(gx, (unsigned)(2 * nfields)), th, sm, stream>>>(ax);
+        e = herm_launch_pass<double, 0>(stream, smem_optin, lqx, ax, (unsigned)(2 * nfields), (int64_t)rows * 2 * nfields);
+        if (e != cudaSuccess) return e;
         *nlaunch += 1;
     }
     return cudaGetLastError();
@@ -397,13 +426,14 @@ inline cudaError_t herm_sharded_ypass(cudaStream_t stream, size_t smem_optin, co
     ay.conj_io = forward_dir ? 0 : 1;
     ay.nlx = g.nlx; ay.nly = g.nly; ay.nrow = nranks * herm_shard_rows(g, nranks); ay.nx = nxl;
     ay.out_off = g.py; ay.n_out = g.ny;
-    ay.twiddle = tab.tw_y; ay.rev = tab.rev_y;
+    ay.twiddle = tab.tw_y; ay.rev = tab.rev_y; ay.tw24 = tab.t24_y;
     ay.nfields_first = nfields;
     ay.in = recv_p; ay.in2 = recv_q; ay.out = out_p; ay.out2 = out_q;
     cudaError_t e = cudaFuncSetAttribute(k_fft_h<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
     if (e != cudaSuccess) return e;
-    k_fft_h<double, 1><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), (unsigned)(2 * nfields)),
-                         fft_pick_threads(ay.N, ay.cw, ay.radix[0]), fft_smem_bytes(ay.N, ay.cw, false), stream>>>(ay);
+    const int lqy = fft_env_int("BLDFM_B200_FFT24", 1) ? fft24_lq(g.nfy, g.nly, g.ny, g.py) : -1;
+    e = herm_launch_pass<double, 1>(stream, smem_optin, lqy, ay, (unsigned)(2 * nfields), (int64_t)ay.ntrans * 2 * nfields);
+    if (e != cudaSuccess) return e;
     *nlaunch += 1;
     return cudaGetLastError();
 }

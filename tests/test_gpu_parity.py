@@ -294,3 +294,35 @@ def test_half_plane_march_equals_full_march(B, shape, modes, halo):
                 assert np.array_equal(hp, fp) and np.array_equal(hq, fq)
             else:
                 assert rel_l2c(hp, fp) <= TOL_F64 and rel_l2c(hq, fq) <= TOL_F64
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (512, 512), (256, 512), (1024, 1024), (2048, 1024), (4096, 4096)])
+def test_default_halo_passes_equal_generic_passes(B, shape):
+    """Default-halo geometry (modes == grid, padded = 3 x grid): the back-transform runs the specialised
+    sparse radix-24 passes (fft24.cuh, Q = 32 ... 512); BLDFM_B200_FFT24=0 forces the generic real-output
+    passes.  Same operands, different factorisation: agreement to round-off."""
+    import os
+    from bldfm_b200.pbl_model import vertical_profiles
+    from bldfm_b200.utils import ideal_source
+    ny, nx = shape
+    dom = (3000.0, 3000.0)
+    z, prof = vertical_profiles(8, 6.0, (3.0, -2.0), ustar=0.4, mol=-200.0)
+    cases = [dict(footprint=True, meas_pt=(1300.0, 1700.0), precision="double", levels=[3, 8])]
+    if nx <= 1024:
+        src = ideal_source((nx, ny), dom, src_loc=(900.0, 2000.0), shape="circle")
+        cases.append(dict(footprint=False, meas_pt=(1500.0, 1200.0), precision="double", levels=8, srf_flx=src))
+        cases.append(dict(footprint=False, meas_pt=(0.0, 0.0), precision="single", levels=[2, 8], srf_flx=src))
+    for case in cases:
+        kw = dict(srf_flx=np.zeros((ny, nx)), z=z, profiles=prof, domain=dom, modes=(nx, ny))
+        kw.update(case)
+        _, c1, f1 = B.steady_state_transport_solver(**kw)
+        c1, f1 = c1.copy(), f1.copy()
+        os.environ["BLDFM_B200_FFT24"] = "0"
+        try:
+            _, c0, f0 = B.steady_state_transport_solver(**kw)
+        finally:
+            del os.environ["BLDFM_B200_FFT24"]
+        tol = 1e-13 if c0.dtype == np.float64 else 2e-6
+        assert c1.dtype == c0.dtype
+        assert rel_l2(c1, c0) <= tol, (case["footprint"], rel_l2(c1, c0))
+        assert rel_l2(f1, f0) <= tol, (case["footprint"], rel_l2(f1, f0))
