@@ -214,11 +214,39 @@ k_fft24(const FftHArgs a)
         const int r = it >> LQ, n1 = it & (Q - 1);
         const int tg = t0 + t;
         Cplx<T> v[8], e = {(T)0, (T)0};
-        if (PASS == 0 && a.hs && tg > 0 && tg < a.nly / 2 && n1 != 0) {
-            // interior of a conjugate-symmetric spectrum: H = S, and f = n1 + Q*n2 sits at column n1 + Q*u
+        if (PASS == 0 && a.hs && tg > 0 && tg < a.nly / 2) {
+            // interior row of a conjugate-symmetric spectrum: H = S, and f = n1 + Q*n2 sits at column
+            // n1 + Q*u.  The Nyquist column (items n1 = 0) has no partner in the retained set:
+            // H[fy][-P/2] = S[fy][-P/2]/2 and H[fy][+P/2] = conj(S[-fy][-P/2])/2.
             const V* row = src + (size_t)tg * a.nlx + n1;
+            const V xe = src[(size_t)(a.nly - tg) * a.nlx + 4 * Q];
 #pragma unroll
             for (int u = 0; u < 8; ++u) { const V x = row[u * Q]; v[u] = {x.x, sgn * x.y}; }
+            if (n1 == 0) {
+                v[4] = {(T)0.5 * v[4].r, (T)0.5 * v[4].i};
+                e = {(T)0.5 * xe.x, sgn * ((T)-0.5 * xe.y)};
+            }
+        } else if (PASS == 1 && (a.nx & 1) == 0) {
+            // column pair (2tg, 2tg+1): f > 0 for u < 4 (rows n1 + Q*u of A), f < 0 for u >= 4 (rows
+            // Q*(8-u) - n1): the packing signs are compile-time; only f = 0 (n1 = 0, u = 0) differs
+            const V* up = src + (size_t)n1 * a.nx + 2 * tg;
+            const V* dn = src + (size_t)(Q - n1) * a.nx + 2 * tg;          // row Q*(8-u) - n1 = (Q - n1) + Q*(7-u)
+            const size_t step = (size_t)Q * a.nx;
+            V x1[9], x2[9];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { x1[u] = up[u * step]; x2[u] = up[u * step + 1]; }
+#pragma unroll
+            for (int u = 4; u < 8; ++u) { x1[u] = dn[(7 - u) * step]; x2[u] = dn[(7 - u) * step + 1]; }
+            x1[8] = src[(size_t)(n1 == 0 ? 4 * Q : n1) * a.nx + 2 * tg];
+            x2[8] = src[(size_t)(n1 == 0 ? 4 * Q : n1) * a.nx + 2 * tg + 1];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = {x1[u].x - x2[u].y, sgn * (x1[u].y + x2[u].x)};        // A1 + i*A2
+#pragma unroll
+            for (int u = 4; u < 8; ++u) v[u] = {x1[u].x + x2[u].y, sgn * (x2[u].x - x1[u].y)};        // conj(A1) + i*conj(A2)
+            if (n1 == 0) {
+                v[0] = {x1[0].x, sgn * x2[0].x};                                                     // A[0] is real
+                e = {x1[8].x - x2[8].y, sgn * (x1[8].y + x2[8].x)};
+            }
         } else {
             Fft24Raw<T> raw[9];
 #pragma unroll
@@ -345,6 +373,8 @@ inline size_t fft24_smem_bytes(int lq, int cw, bool f32)
 inline int fft24_pick_cw(int lq, bool f32, size_t smem_optin, int want, int64_t ntrans_total, int num_sms = 148)
 {
     int cw = want;
+    const int forced = fft_env_int(want == 4 ? "BLDFM_FFT24_CW_Y" : "BLDFM_FFT24_CW_X", 0);   // tuning sweeps
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) cw = forced;
     const size_t ctas = lq <= 6 ? 2 : 1;                    // resident CTAs per SM the launch bounds aim at
     while (cw > 1 && fft24_smem_bytes(lq, cw, f32) * ctas > smem_optin) cw >>= 1;
     while (cw > 1 && ntrans_total / cw < 2 * (int64_t)num_sms) cw >>= 1;
@@ -357,7 +387,10 @@ inline cudaError_t fft24_launch_pass(cudaStream_t stream, size_t smem_optin, int
     const bool f32 = sizeof(T) == 4;
     const size_t sm = fft24_smem_bytes(lq, a.cw, f32);
     const int items = a.cw * 3 * (1 << lq);
-    const int threads = std::min(kFft24Threads, std::max(96, (items + 31) / 32 * 32));
+    // pass X of the radix-16 plans (150 registers) runs best as two resident CTAs of 192 threads (measured)
+    const int tdef = (PASS == 0 && lq >= 7 && lq <= 8) ? 192 : kFft24Threads;
+    const int tmax = std::min(kFft24Threads, std::max(64, fft_env_int(PASS == 1 ? "BLDFM_FFT24_THREADS_Y" : "BLDFM_FFT24_THREADS_X", tdef) / 32 * 32));
+    const int threads = std::min(tmax, std::max(96, (items + 31) / 32 * 32));
 #define BLDFM_FFT24_CASE(LQ)                                                                                  \
     case LQ: {                                                                                                \
         cudaError_t e = cudaFuncSetAttribute(k_fft24<T, PASS, LQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
