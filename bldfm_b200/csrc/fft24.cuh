@@ -207,6 +207,11 @@ k_fft24(const FftHArgs a)
     const T sgn = a.conj_io ? (T)-1 : (T)1;
     const V* tw = reinterpret_cast<const V*>(a.tw24);    // [24][Q] | [Q] | [Q/r0]
 
+    // programmatic dependent launch: this grid may have been started while its producer (the march, or
+    // pass X) was still draining; let the next pass do the same, then wait for the producer's results
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
+
     // ---- stage 1: sparse radix-24 from global memory, item = (n1, r) -> outputs k2 = r + 3q
     for (int idx = threadIdx.x; idx < cw * 3 * Q; idx += (int)blockDim.x) {
         int t, it;
@@ -385,6 +390,8 @@ template <typename T, int PASS>
 inline cudaError_t fft24_launch_pass(cudaStream_t stream, size_t smem_optin, int lq, const FftHArgs& a, dim3 grid)
 {
     const bool f32 = sizeof(T) == 4;
+    // overlap this grid's launch with the tail of the kernel before it in the stream (see k_fft24)
+    static const bool pdl = fft_env_int("BLDFM_B200_PDL", 1) != 0;
     const size_t sm = fft24_smem_bytes(lq, a.cw, f32);
     const int items = a.cw * 3 * (1 << lq);
     // pass X of the radix-16 plans (150 registers) runs best as two resident CTAs of 192 threads (measured)
@@ -396,7 +403,14 @@ inline cudaError_t fft24_launch_pass(cudaStream_t stream, size_t smem_optin, int
         cudaError_t e = cudaFuncSetAttribute(k_fft24<T, PASS, LQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                              (int)smem_optin);                                                \
         if (e != cudaSuccess) return e;                                                                       \
-        k_fft24<T, PASS, LQ><<<grid, threads, sm, stream>>>(a);                                               \
+        cudaLaunchConfig_t cfg = {};                                                                          \
+        cfg.gridDim = grid; cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = sm; cfg.stream = stream; \
+        cudaLaunchAttribute at[1];                                                                            \
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                        \
+        at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;                                       \
+        cfg.attrs = at; cfg.numAttrs = 1;                                                                     \
+        e = cudaLaunchKernelEx(&cfg, k_fft24<T, PASS, LQ>, a);                                                \
+        if (e != cudaSuccess) return e;                                                                       \
         break;                                                                                                \
     }
     switch (lq) {

@@ -312,6 +312,9 @@ k_march(const MarchArgs a)
     LevelCoef* sc = reinterpret_cast<LevelCoef*>(smem_raw);
     int32_t* srow = reinterpret_cast<int32_t*>(sc + a.coef_stride);
 
+    // the back-transform that follows may be launched as soon as every CTA of this grid is resident; its
+    // CTAs start when ours retire and wait for the spectra in cudaGridDependencySynchronize()
+    cudaTriggerProgrammaticLaunchCompletion();
     const GroupDesc gd = a.groups[blockIdx.y];
     const int S = gd.S;
     {

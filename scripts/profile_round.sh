@@ -11,6 +11,6 @@ cat gpurun_out/march_scaling_${TAG}.jsonl | cut -c1-300
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 # full capture: 3rd march launch and the two back-transform passes after it
-ncu --set full --clock-control none --import-source on -k regex:'k_march|k_fft_h' -s 6 -c 3 -f \
+ncu --set full --clock-control none --import-source on -k regex:'k_march|k_fft' -s 6 -c 3 -f \
     -o gpurun_out/hot_${TAG} python bench.py --steps 6 --warmup 3 --no-cpu > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out | tail -8
