@@ -1082,7 +1082,9 @@ int bldfm_solve_batched_measure(bldfm_plan* pl, int32_t nprob, const bldfm_probl
     pl->launches += 3;
     CUDA_TRY(cudaMemcpyAsync(conc_w, result, (size_t)nfields * sizeof(double), cudaMemcpyDeviceToHost, pl->stream));
     CUDA_TRY(cudaMemcpyAsync(flx_w, result + nfields, (size_t)nfields * sizeof(double), cudaMemcpyDeviceToHost, pl->stream));
-    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    // BLDFM_ASYNC: conc_w / flx_w must be pinned and are valid after bldfm_plan_synchronize(); the next
+    // batch (same stream, so its kernels are ordered after these copies) can be enqueued meanwhile
+    if (!(flags & BLDFM_ASYNC)) CUDA_TRY(cudaStreamSynchronize(pl->stream));
     return BLDFM_OK;
 }
 

@@ -225,12 +225,15 @@ def synchronize():
 
 
 def measure_batched(weight, srf_flx, zs, profiles_list, domain, levels, modes=(512, 512), meas_pts=None,
-                    srf_bg_conc=0.0, footprint=False, analytic=False, halo=None, precision="single"):
+                    srf_bg_conc=0.0, footprint=False, analytic=False, halo=None, precision="single", wait=True):
     """``point_measurement`` (utils.py:80-92) fused on the device for a batch of solves.
 
     Returns ``(conc_w, flx_w)`` of shape ``[B, nlv]``: ``sum(conc[b, l] * weight)`` and
     ``sum(flx[b, l] * weight)``.  With ``footprint=True`` and ``weight`` = surface flux map, ``flx_w`` is
     the flux each tower measures -- 8 bytes per footprint cross PCIe instead of the 4 MB field.
+
+    ``wait=False`` only enqueues the batch: the returned (pinned) arrays are valid after ``synchronize()``,
+    and the host can prepare the next batch while this one runs.
     """
     q0 = np.asarray(srf_flx)
     B = len(zs)
@@ -249,8 +252,13 @@ def measure_batched(weight, srf_flx, zs, profiles_list, domain, levels, modes=(5
         p, k = _lib.make_problem(zs[b], profiles_list[b], meas_pts[b], bg[b])
         probs.append(p)
         keep.append(k)
-    conc_w = np.empty((B, nlv))
-    flx_w = np.empty((B, nlv))
+    if wait:
+        conc_w = np.empty((B, nlv))
+        flx_w = np.empty((B, nlv))
+    else:
+        conc_w = _pinned_pool.empty((B, nlv), np.float64)
+        flx_w = _pinned_pool.empty((B, nlv), np.float64)
+        flags |= _lib.ASYNC
     src = None if footprint else _lib.as_f64(q0)
     parr = (_lib.Problem * B)(*probs)
     plan = get_fft_manager().plan(geom)

@@ -143,7 +143,8 @@ int  bldfm_solve_batched(bldfm_plan *plan, int32_t nprob, const bldfm_problem *p
  * level row r returns sum_{y,x} conc[b][r][y][x]*weight[y][x] and the same for flx -- what
  * point_measurement(f, g) (src/bldfm/utils.py:80-92) computes per footprint on the host.
  *   weight        host [ny][nx] float64 (e.g. the surface flux map)
- *   conc_w, flx_w host [nprob][nlv] float64. */
+ *   conc_w, flx_w host [nprob][nlv] float64.  With BLDFM_ASYNC the call only enqueues: conc_w/flx_w must
+ *                 then be PINNED and are valid after bldfm_plan_synchronize(). */
 int  bldfm_solve_batched_measure(bldfm_plan *plan, int32_t nprob, const bldfm_problem *probs,
                                  const int64_t *levels, int32_t nlv, const double *srf_flx, int flags,
                                  const double *weight, double *conc_w, double *flx_w);

@@ -77,8 +77,8 @@ def main():
     dev_f = torch.empty_like(dev_c)
     host_c = torch.empty((4, B, n, n), dtype=torch.float64).pin_memory()
     host_f = torch.empty((4, B, n, n), dtype=torch.float64).pin_memory()
-    wq = np.empty((B, 1))
-    wf = np.empty((B, 1))
+    wq = torch.empty((4, B, 1), dtype=torch.float64).pin_memory()
+    wf = torch.empty((4, B, 1), dtype=torch.float64).pin_memory()
     zeros = np.zeros((n, n))
 
     def problems(groups):
@@ -101,8 +101,12 @@ def main():
         for c0 in range(0, len(mine), args.chunk):
             parr, keep, nb = problems(mine[c0:c0 + args.chunk])
             if mode == "measure":
-                _lib.check(L.bldfm_solve_batched_measure(plan, nb, parr, lvp, 1, None, base, _lib.ptr(flux_map),
-                                                         _lib.ptr(wq), _lib.ptr(wf)))
+                # enqueue-only with a ring of 4 pinned result pairs: the host prepares the next chunk meanwhile
+                if (c0 // args.chunk) % 4 == 3:
+                    _lib.check(L.bldfm_plan_synchronize(plan))
+                _lib.check(L.bldfm_solve_batched_measure(plan, nb, parr, lvp, 1, None, base | _lib.ASYNC,
+                                                         _lib.ptr(flux_map), wq[slot].data_ptr(), wf[slot].data_ptr()))
+                slot = (slot + 1) % 4
             elif mode == "host":
                 # pinned ring of 4 result sets; enqueue-only: the D2H of this chunk overlaps the next compute
                 if (c0 // args.chunk) % 4 == 3:

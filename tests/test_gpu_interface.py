@@ -105,3 +105,9 @@ def test_measure_batched_equals_point_measurement(gpu_lib):
         for l in range(2):
             assert abs(fw[b, l] - point_measurement(flx[b, l], flux_map)) <= 1e-12 * abs(fw[b, l])
             assert abs(cw[b, l] - point_measurement(conc[b, l], flux_map)) <= 1e-12 * abs(cw[b, l])
+    # enqueue-only variant: results land in pinned arrays, valid after synchronize()
+    cw2, fw2 = bldfm_b200.measure_batched(flux_map, np.zeros((48, 64)), zs, profs, meas_pts=pts, wait=False, **kw)
+    cw3, fw3 = bldfm_b200.measure_batched(2.0 * flux_map, np.zeros((48, 64)), zs, profs, meas_pts=pts, wait=False, **kw)
+    bldfm_b200.solver.synchronize()
+    assert np.array_equal(cw2, cw) and np.array_equal(fw2, fw)
+    assert np.allclose(fw3, 2.0 * fw, rtol=1e-13, atol=0.0)
