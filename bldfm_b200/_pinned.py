@@ -36,6 +36,11 @@ class _Pool:
             self.outstanding -= nbytes
             self.free[nbytes].append(ptr)
 
+    def empty2(self, shape, dtype):
+        """(array, pinned): like ``empty`` but also tells whether the array really is page-locked."""
+        a = self.empty(shape, dtype)
+        return a, a.base is not None
+
     def empty(self, shape, dtype):
         """np.empty(shape, dtype) on pinned memory when possible."""
         dtype = np.dtype(dtype)

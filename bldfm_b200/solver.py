@@ -147,21 +147,24 @@ def steady_state_transport_solver(
     prob, keep = _lib.make_problem(z, profiles, meas_pt, srf_bg_conc)
     f32 = bool(_lib.lib().bldfm_output_is_f32(flags, prob.xm, prob.ym))
     dt = np.float32 if f32 else np.float64
-    both = _pinned_pool.empty((2, nlv, ny, nx), dt)
+    both, pinned = _pinned_pool.empty2((2, nlv, ny, nx), dt)
     conc, flx = both[0], both[1]
     src = None
     if not footprint:
         src = _lib.as_f64(q0)
 
     plan = get_fft_manager().plan(geom)
-    rc = _lib.lib().bldfm_solve(
+    L = _lib.lib()
+    # page-locked outputs: enqueue only, build the grid while the GPU works, then wait for the results
+    rc = L.bldfm_solve(
         plan, C.byref(prob), lv64.ctypes.data_as(C.POINTER(C.c_int64)), nlv,
-        None if src is None else _lib.ptr(src), flags, _lib.ptr(conc), _lib.ptr(flx))
+        None if src is None else _lib.ptr(src), flags | (_lib.ASYNC if pinned else 0), _lib.ptr(conc), _lib.ptr(flx))
     _lib.check(rc)
-    del keep
-
     grid = make_grid(z, lv, domain, nx, ny)
     result = (grid, np.squeeze(conc), np.squeeze(flx))
+    if pinned:
+        _lib.check(L.bldfm_plan_synchronize(plan))
+    del keep
 
     if cache is not None and footprint:                                    # solver.py:301-302
         cache.put(z, profiles, domain, modes, meas_pt, halo, precision, *result)
