@@ -78,6 +78,21 @@ def _levels_array(levels):
     return lv, np.ascontiguousarray(lv, dtype=np.int64)
 
 
+_LEVEL_PTR = {}
+
+
+def _levels_ptr(lv64):
+    """ctypes pointer to an int64 level array; memoised for the cached scalar-level arrays."""
+    key = id(lv64)
+    hit = _LEVEL_PTR.get(key)
+    if hit is not None and hit[0] is lv64:
+        return hit[1]
+    p = lv64.ctypes.data_as(C.POINTER(C.c_int64))
+    if len(_LEVEL_PTR) < 1024 and any(v[1] is lv64 for v in _LEVEL_CACHE.values()):
+        _LEVEL_PTR[key] = (lv64, p)
+    return p
+
+
 _XY_CACHE = {}
 
 
@@ -145,7 +160,8 @@ def steady_state_transport_solver(
     nlv = len(lv64)
 
     prob, keep = _lib.make_problem(z, profiles, meas_pt, srf_bg_conc)
-    f32 = bool(_lib.lib().bldfm_output_is_f32(flags, prob.xm, prob.ym))
+    # dtype rule of solver.py:177-185,254-262 (the C side applies the same one: bldfm_output_is_f32)
+    f32 = precision == "single" and not footprint and not (prob.xm * prob.xm + prob.ym * prob.ym > 0.0)
     dt = np.float32 if f32 else np.float64
     both, pinned = _pinned_pool.empty2((2, nlv, ny, nx), dt)
     conc, flx = both[0], both[1]
@@ -155,10 +171,12 @@ def steady_state_transport_solver(
 
     plan = get_fft_manager().plan(geom)
     L = _lib.lib()
+    # one address lookup for both outputs (taking an array's address from Python costs microseconds);
     # page-locked outputs: enqueue only, build the grid while the GPU works, then wait for the results
+    base = both.ctypes.data
     rc = L.bldfm_solve(
-        plan, C.byref(prob), lv64.ctypes.data_as(C.POINTER(C.c_int64)), nlv,
-        None if src is None else _lib.ptr(src), flags | (_lib.ASYNC if pinned else 0), _lib.ptr(conc), _lib.ptr(flx))
+        plan, C.byref(prob), _levels_ptr(lv64), nlv,
+        None if src is None else _lib.ptr(src), flags | (_lib.ASYNC if pinned else 0), base, base + conc.nbytes)
     _lib.check(rc)
     grid = make_grid(z, lv, domain, nx, ny)
     result = (grid, np.squeeze(conc), np.squeeze(flx))

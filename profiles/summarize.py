@@ -44,13 +44,27 @@ def launches(path):
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
         v = float(row["Metric Value"].replace(",", ""))
-        agg.setdefault(row["Kernel Name"], []).append(v)
+        agg.setdefault((row["Kernel Name"], row.get("Grid Size", "")), []).append(v)
     tot = sum(sum(v) for v in agg.values())
     print(f"# ncu --metrics gpu__time_duration.sum --clock-control none  ({path})")
     print("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes")
-    print(f"{'kernel':100s} {'n':>5s} {'avg_us':>10s} {'share%':>7s}")
-    for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
-        print(f"{k[:100]:100s} {len(v):5d} {sum(v)/len(v)/1e3:10.2f} {sum(v)/tot*100:7.1f}")
+    print(f"{'kernel':84s} {'grid':>16s} {'n':>5s} {'avg_us':>10s} {'share%':>7s}")
+    for (k, g), v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
+        print(f"{k[:84]:84s} {g:>16s} {len(v):5d} {sum(v)/len(v)/1e3:10.2f} {sum(v)/tot*100:7.1f}")
+    # the single-solve step of bench.py: one march launch + the back-transform launches that follow it
+    step = collections.OrderedDict()
+    for (k, g), v in agg.items():
+        if "bldfm::" in k and g.endswith(", 1, 1)") and "k_march" in k:
+            step[k] = sum(v) / len(v)
+            n_single = len(v)
+    for (k, g), v in agg.items():
+        if "bldfm::" in k and "k_march" not in k and step and len(v) == n_single:
+            step[k + " " + g] = sum(v) / len(v)
+    if step:
+        t = sum(step.values())
+        print("# single-solve step (config 2): kernel shares")
+        for k, v in step.items():
+            print(f"#   {k[:90]:90s} {v/1e3:8.2f} us {v/t*100:6.1f} %")
 
 
 def kernel(path):
