@@ -23,6 +23,7 @@
 #include "fft.cuh"
 #include "fft_herm.cuh"
 #include "fft24.cuh"
+#include "fft48.cuh"
 
 using namespace bldfm;
 
@@ -115,6 +116,8 @@ struct bldfm_plan {
     DevBuf tw64, tw32;       // pruned path: twiddle tables  x[nfx] | y[nfy]  (double2 / float2)
     DevBuf t24_64, t24_32;   // fft24.cuh tables  x | y  (only for N = 3P passes)
     size_t t24_off_y[2] = {0, 0};
+    DevBuf t48_64, t48_32;   // fft48.cuh tables  x | y  (P = 256, 512)
+    size_t t48_off_y[2] = {0, 0};
     DevBuf out_c, out_f;     // device outputs when the caller wants host results (set 0)
     DevBuf out_c2, out_f2;   // second set: D2H of one solve overlaps the compute of the next
     int out_set = 0;
@@ -340,6 +343,26 @@ int ensure_twiddles(bldfm_plan* pl, bool f32, PrunedFftTables* tab)
         }
         if (lqx >= 0) tab->t24_x = b24.p;
         if (lqy >= 0) tab->t24_y = static_cast<const char*>(b24.p) + pl->t24_off_y[f32 ? 1 : 0];
+    }
+    const int l48x = fft48_lq(g.nfx, g.nlx, g.nx, g.px), l48y = fft48_lq(g.nfy, g.nly, g.ny, g.py);
+    if (l48x >= 0 || l48y >= 0) {
+        DevBuf& b48 = f32 ? pl->t48_32 : pl->t48_64;
+        if (!b48.p) {
+            std::vector<double> tx, ty;
+            if (l48x >= 0) fft48_tables(l48x, tx);
+            if (l48y >= 0) fft48_tables(l48y, ty);
+            pl->t48_off_y[f32 ? 1 : 0] = tx.size() / 2 * esz;
+            tx.insert(tx.end(), ty.begin(), ty.end());
+            TRY(b48.ensure(tx.size() / 2 * esz));
+            if (f32) {
+                std::vector<float> tf(tx.begin(), tx.end());
+                CUDA_TRY(cudaMemcpy(b48.p, tf.data(), tf.size() * sizeof(float), cudaMemcpyHostToDevice));
+            } else {
+                CUDA_TRY(cudaMemcpy(b48.p, tx.data(), tx.size() * sizeof(double), cudaMemcpyHostToDevice));
+            }
+        }
+        if (l48x >= 0) tab->t48_x = b48.p;
+        if (l48y >= 0) tab->t48_y = static_cast<const char*>(b48.p) + pl->t48_off_y[f32 ? 1 : 0];
     }
     return BLDFM_OK;
 }
@@ -954,7 +977,7 @@ int bldfm_plan_destroy(bldfm_plan* pl)
     pl->tables.release(); pl->params.release(); pl->spec_p.release(); pl->spec_q.release();
     pl->pad_in.release(); pl->pad_out.release(); pl->src_in.release(); pl->src_pad.release();
     pl->weight.release(); pl->partial.release();
-    pl->fft_work.release(); pl->tw64.release(); pl->tw32.release(); pl->t24_64.release(); pl->t24_32.release(); pl->out_c.release(); pl->out_f.release();
+    pl->fft_work.release(); pl->tw64.release(); pl->tw32.release(); pl->t24_64.release(); pl->t24_32.release(); pl->t48_64.release(); pl->t48_32.release(); pl->out_c.release(); pl->out_f.release();
     for (auto& s : pl->staging) {
         if (s.host) cudaFreeHost(s.host);
         if (s.done) cudaEventDestroy(s.done);

@@ -487,6 +487,8 @@ struct PrunedFftTables {
     const int32_t* rev_y = nullptr;
     const void* t24_x = nullptr;  // lane-contiguous twiddle tables of the N = 3P passes (fft24.cuh), or NULL
     const void* t24_y = nullptr;
+    const void* t48_x = nullptr;  // stage-1 table of the two-stage variant (fft48.cuh), or NULL
+    const void* t48_y = nullptr;
 };
 
 // Runs both passes for the `nfields` compact spectra of spec_p (-> out_p) and of spec_q (-> out_q)

@@ -44,6 +44,7 @@ struct FftHArgs {
     const void* twiddle;
     const int32_t* rev;
     const void* tw24;          // fft24.cuh: [24][Q] stage-1 table | [Q] | [Q/r0] in-place stage tables
+    const void* tw48;          // fft48.cuh: [48][Q] stage-1 table
 };
 
 // S[fy][fx] with zero outside the retained set (signed frequencies)
@@ -283,6 +284,11 @@ inline int fft24_lq(int N, int nl, int n, int p);
 inline int fft24_pick_cw(int lq, bool f32, size_t smem_optin, int want, int64_t ntrans_total, int num_sms);
 template <typename T, int PASS>
 inline cudaError_t fft24_launch_pass(cudaStream_t stream, size_t smem_optin, int lq, const FftHArgs& a, dim3 grid);
+// two-stage variant for P = 256, 512 (fft48.cuh)
+inline int fft48_lq(int N, int nl, int n, int p);
+inline int fft48_pick_cw(int lq, bool f32, size_t smem_optin, int want, int64_t ntrans_total, int num_sms);
+template <typename T, int PASS>
+inline cudaError_t fft48_launch_pass(cudaStream_t stream, size_t smem_optin, int lq, const FftHArgs& a, dim3 grid);
 
 // launch one pass with the specialised kernel when its geometry allows (lq >= 0), else with k_fft_h
 template <typename T, int PASS>
@@ -290,6 +296,16 @@ inline cudaError_t herm_launch_pass(cudaStream_t stream, size_t smem_optin, int 
                                     int64_t ntrans_total)
 {
     const bool f32 = sizeof(T) == 4;
+    // lq >= 0 implies N = 3P with P = nlx = n_out = out_off: try the two-stage variant first
+    // (measured: 5 % faster than fft24.cuh when the launch fills the GPU many times over, 2 % slower for the
+    // ~500 transforms of a single solve -> used for large launches only; BLDFM_B200_FFT48 = 0 never, 2 always)
+    const int mode48 = fft_env_int("BLDFM_B200_FFT48", 1);
+    const bool want48 = mode48 == 2 || (mode48 == 1 && ntrans_total >= 4096);
+    const int lq48 = (lq >= 0 && a.tw48 && want48) ? fft48_lq(a.N, a.n_out, a.n_out, a.out_off) : -1;
+    if (lq48 >= 0) {
+        a.cw = fft48_pick_cw(lq48, f32, smem_optin, PASS == 1 ? 4 : 2, ntrans_total, 148);
+        return fft48_launch_pass<T, PASS>(stream, smem_optin, lq48, a, dim3((unsigned)((a.ntrans + a.cw - 1) / a.cw), nfields_y));
+    }
     if (lq >= 0 && a.tw24) {
         a.cw = fft24_pick_cw(lq, f32, smem_optin, PASS == 1 ? 4 : 2, ntrans_total, 148);
         return fft24_launch_pass<T, PASS>(stream, smem_optin, lq, a, dim3((unsigned)((a.ntrans + a.cw - 1) / a.cw), nfields_y));
@@ -320,7 +336,7 @@ inline cudaError_t herm_fft_launch(cudaStream_t stream, size_t smem_optin, const
     ax.ntrans = nrow; ax.conj_io = forward_dir ? 0 : 1;
     ax.nlx = g.nlx; ax.nly = g.nly; ax.nrow = nrow; ax.nx = g.nx;
     ax.out_off = g.px; ax.n_out = g.nx;
-    ax.twiddle = tab.tw_x; ax.rev = tab.rev_x; ax.tw24 = tab.t24_x;
+    ax.twiddle = tab.tw_x; ax.rev = tab.rev_x; ax.tw24 = tab.t24_x; ax.tw48 = tab.t48_x;
     ax.hs = herm_spec ? 1 : 0;
     const bool use24 = fft_env_int("BLDFM_B200_FFT24", 1) != 0;
     const int lqx = use24 ? fft24_lq(g.nfx, g.nlx, g.nx, g.px) : -1;
@@ -332,7 +348,7 @@ inline cudaError_t herm_fft_launch(cudaStream_t stream, size_t smem_optin, const
     ay.cw = fft_pick_cw(g.nfy, f32, smem_optin, 4, (int64_t)((g.nx + 1) / 2) * 2 * nfields);
     ay.ntrans = (g.nx + 1) / 2;
     ay.out_off = g.py; ay.n_out = g.ny;
-    ay.twiddle = tab.tw_y; ay.rev = tab.rev_y; ay.tw24 = tab.t24_y;
+    ay.twiddle = tab.tw_y; ay.rev = tab.rev_y; ay.tw24 = tab.t24_y; ay.tw48 = tab.t48_y;
 
     cudaError_t e;
     e = cudaFuncSetAttribute(k_fft_h<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
@@ -383,7 +399,7 @@ inline cudaError_t herm_sharded_xpass(cudaStream_t stream, size_t smem_optin, co
     ax.ntrans = rows; ax.conj_io = forward_dir ? 0 : 1;
     ax.nlx = g.nlx; ax.nly = g.nly; ax.nrow = g.nly / 2 + 1; ax.nx = g.nx;
     ax.out_off = g.px; ax.n_out = g.nx;
-    ax.twiddle = tab.tw_x; ax.rev = tab.rev_x; ax.tw24 = tab.t24_x;
+    ax.twiddle = tab.tw_x; ax.rev = tab.rev_x; ax.tw24 = tab.t24_x; ax.tw48 = tab.t48_x;
     ax.row0 = row0; ax.out_block = nxl;
     ax.out_field_stride = (int64_t)nranks * Rp * nxl;
     ax.out_block_stride = (int64_t)Rp * nxl;
@@ -426,7 +442,7 @@ inline cudaError_t herm_sharded_ypass(cudaStream_t stream, size_t smem_optin, co
     ay.conj_io = forward_dir ? 0 : 1;
     ay.nlx = g.nlx; ay.nly = g.nly; ay.nrow = nranks * herm_shard_rows(g, nranks); ay.nx = nxl;
     ay.out_off = g.py; ay.n_out = g.ny;
-    ay.twiddle = tab.tw_y; ay.rev = tab.rev_y; ay.tw24 = tab.t24_y;
+    ay.twiddle = tab.tw_y; ay.rev = tab.rev_y; ay.tw24 = tab.t24_y; ay.tw48 = tab.t48_y;
     ay.nfields_first = nfields;
     ay.in = recv_p; ay.in2 = recv_q; ay.out = out_p; ay.out2 = out_q;
     cudaError_t e = cudaFuncSetAttribute(k_fft_h<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);

@@ -7,6 +7,7 @@ ext "k_marchILb0ELb0" profiles/sass_march_exact.txt
 ext "k_marchILb1ELb0" profiles/sass_march_fma.txt
 ext "k_fft24IdLi0ELi6" profiles/sass_fft24_passX_c128_q64.txt
 ext "k_fft24IdLi1ELi6" profiles/sass_fft24_passY_c128_q64.txt
+ext "k_fft48IdLi0ELi5" profiles/sass_fft48_passX_c128_q32.txt
 ext "k_fft_hIdLi0E" profiles/sass_fft_h_passX_c128.txt
 ext "k_fft_hIdLi1E" profiles/sass_fft_h_passY_c128.txt
 wc -l profiles/sass_*.txt

@@ -299,8 +299,9 @@ def test_half_plane_march_equals_full_march(B, shape, modes, halo):
 @pytest.mark.parametrize("shape", [(256, 256), (512, 512), (256, 512), (1024, 1024), (2048, 1024), (4096, 4096)])
 def test_default_halo_passes_equal_generic_passes(B, shape):
     """Default-halo geometry (modes == grid, padded = 3 x grid): the back-transform runs the specialised
-    sparse radix-24 passes (fft24.cuh, Q = 32 ... 512); BLDFM_B200_FFT24=0 forces the generic real-output
-    passes.  Same operands, different factorisation: agreement to round-off."""
+    sparse radix-24 passes (fft24.cuh, Q = 32 ... 512) or, for large launches, the sparse radix-48 passes
+    (fft48.cuh); BLDFM_B200_FFT24=0 forces the generic real-output passes.  Same operands, different
+    factorisations: agreement to round-off."""
     import os
     from bldfm_b200.pbl_model import vertical_profiles
     from bldfm_b200.utils import ideal_source
@@ -317,6 +318,13 @@ def test_default_halo_passes_equal_generic_passes(B, shape):
         kw.update(case)
         _, c1, f1 = B.steady_state_transport_solver(**kw)
         c1, f1 = c1.copy(), f1.copy()
+        # the two-stage variant (fft48.cuh, P = 256 / 512) is picked for large launches only: force it
+        os.environ["BLDFM_B200_FFT48"] = "2"
+        try:
+            _, c2, f2 = B.steady_state_transport_solver(**kw)
+            c2, f2 = c2.copy(), f2.copy()
+        finally:
+            del os.environ["BLDFM_B200_FFT48"]
         os.environ["BLDFM_B200_FFT24"] = "0"
         try:
             _, c0, f0 = B.steady_state_transport_solver(**kw)
@@ -326,3 +334,5 @@ def test_default_halo_passes_equal_generic_passes(B, shape):
         assert c1.dtype == c0.dtype
         assert rel_l2(c1, c0) <= tol, (case["footprint"], rel_l2(c1, c0))
         assert rel_l2(f1, f0) <= tol, (case["footprint"], rel_l2(f1, f0))
+        assert rel_l2(c2, c0) <= tol, (case["footprint"], rel_l2(c2, c0))
+        assert rel_l2(f2, f0) <= tol, (case["footprint"], rel_l2(f2, f0))
