@@ -382,7 +382,12 @@ inline int fft24_pick_cw(int lq, bool f32, size_t smem_optin, int want, int64_t 
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8) cw = forced;
     const size_t ctas = lq <= 6 ? 2 : 1;                    // resident CTAs per SM the launch bounds aim at
     while (cw > 1 && fft24_smem_bytes(lq, cw, f32) * ctas > smem_optin) cw >>= 1;
-    while (cw > 1 && ntrans_total / cw < 2 * (int64_t)num_sms) cw >>= 1;
+    if (forced > 0) return cw;
+    // small launches: keep enough CTAs to cover the SMs -- twice over for pass X; pass Y (want == 4) gains
+    // more from two column pairs per CTA (full 32-byte store sectors, 64-byte loads) than from the extra CTAs
+    // (measured at config 2, 512 transforms: cw = 2 -> 19.2 us for both passes, cw = 1 -> 23.4 us)
+    const int64_t min_ctas = want == 4 ? (3 * (int64_t)num_sms) / 2 : 2 * (int64_t)num_sms;
+    while (cw > 1 && ntrans_total / cw < min_ctas) cw >>= 1;
     return cw;
 }
 
