@@ -93,60 +93,6 @@ template <> struct Fft24Plan<7> { static constexpr int n = 2, r0 = 16, r1 = 8, r
 template <> struct Fft24Plan<8> { static constexpr int n = 2, r0 = 16, r1 = 16, r2 = 1; };
 template <> struct Fft24Plan<9> { static constexpr int n = 3, r0 = 8, r1 = 8, r2 = 8; };
 
-// Operand loads are split in two steps so that the eight (sixteen) global loads of an item are all in
-// flight before the first one is consumed: `fetch` is branch-free (out-of-range elements read a valid
-// dummy address and are zeroed by a select), `combine` is pure arithmetic.
-template <typename T> struct Fft24Raw { typename Vec2<T>::type a, b; int flag; };
-
-// pass X operand H[fy][f] = (S[fy][f] + conj(S[-fy][-f]))/2 for a signed frequency f, fy >= 0
-template <typename T>
-__device__ __forceinline__ Fft24Raw<T> fft24_fetch_x(const FftHArgs& a, const typename Vec2<T>::type* __restrict__ S, int fy, int f)
-{
-    const int hx = a.nlx / 2, hy = a.nly / 2, px = (a.nlx - 1) / 2, py = (a.nly - 1) / 2;
-    // conjugate-symmetric spectrum (half-plane march): in the interior the two terms are equal bit for bit
-    const bool one = a.hs && f > -hx && f < hx && fy > 0 && fy < hy;
-    const bool ok1 = fy <= py && f >= -hx && f <= px;                   // S[fy][f] is a retained mode
-    const bool ok2 = !one && fy <= hy && -f >= -hx && -f <= px;         // S[-fy][-f] is one
-    const int i1 = ok1 ? fy * a.nlx + (f >= 0 ? f : f + a.nlx) : 0;
-    const int i2 = ok2 ? (fy > 0 ? a.nly - fy : 0) * a.nlx + (f > 0 ? a.nlx - f : -f) : i1;
-    Fft24Raw<T> r;
-    r.a = S[i1];
-    r.b = S[i2];
-    r.flag = (one ? 4 : 0) | (ok1 ? 1 : 0) | (ok2 ? 2 : 0);
-    return r;
-}
-
-template <typename T>
-__device__ __forceinline__ Cplx<T> fft24_combine_x(const Fft24Raw<T>& r)
-{
-    const T ax = (r.flag & 1) ? r.a.x : (T)0, ay = (r.flag & 1) ? r.a.y : (T)0;
-    const T bx = (r.flag & 2) ? r.b.x : (T)0, by = (r.flag & 2) ? r.b.y : (T)0;
-    const Cplx<T> h = {(T)0.5 * (ax + bx), (T)0.5 * (ay - by)};
-    return (r.flag & 4) ? Cplx<T>{r.a.x, r.a.y} : h;
-}
-
-// pass Y operand of the column pair (x1, x1+1) for a signed frequency f, |f| <= nly/2
-template <typename T>
-__device__ __forceinline__ Fft24Raw<T> fft24_fetch_y(const FftHArgs& a, const typename Vec2<T>::type* __restrict__ A, int x1, int f)
-{
-    const int af = f >= 0 ? f : -f;
-    const bool pair = x1 + 1 < a.nx;
-    Fft24Raw<T> r;
-    r.a = A[(size_t)af * a.nx + x1];
-    r.b = A[(size_t)af * a.nx + x1 + (pair ? 1 : 0)];
-    r.flag = (pair ? 1 : 0) | (f == 0 ? 2 : 0) | (f < 0 ? 4 : 0);
-    return r;
-}
-
-template <typename T>
-__device__ __forceinline__ Cplx<T> fft24_combine_y(const Fft24Raw<T>& r)
-{
-    const T bx = (r.flag & 1) ? r.b.x : (T)0, by = (r.flag & 1) ? r.b.y : (T)0;
-    if (r.flag & 2) return {r.a.x, bx};                      // A[0] is real
-    const T sg = (r.flag & 4) ? (T)-1 : (T)1;                // f > 0: A1 + i*A2 ; f < 0: conj(A1) + i*conj(A2)
-    return {r.a.x - sg * by, sg * r.a.y + bx};
-}
-
 // split a flat work index into (transform, item): pass X keeps the items of one transform on
 // consecutive lanes (contiguous global rows), pass Y the column pairs (contiguous 16/32-byte pieces)
 template <int PASS>
