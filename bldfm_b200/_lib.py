@@ -47,6 +47,7 @@ EXPORTS = [
     "bldfm_host_alloc", "bldfm_host_free", "bldfm_device_alloc", "bldfm_device_free",
     "bldfm_memcpy_d2h", "bldfm_memcpy_h2d", "bldfm_fp64_peak",
     "bldfm_solve_batched_measure", "bldfm_sharded_stage1", "bldfm_sharded_stage2", "bldfm_ipc_export", "bldfm_ipc_open", "bldfm_ipc_close",
+    "bldfm_march_coverage",
 ]
 
 
@@ -126,6 +127,7 @@ def lib():
         "bldfm_solve_spectral": (C.c_int, [vp, PP, I64P, i32, vp, C.c_int, vp, vp]),
         "bldfm_march": (C.c_int, [C.c_int, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, I64P,
                                   vp, vp, C.c_int, vp, vp, vp, vp]),
+        "bldfm_march_coverage": (C.c_int, [C.POINTER(Geometry), i32, i32, i32, vp, C.POINTER(i64)]),
         "bldfm_host_alloc": (C.c_int, [i64, C.POINTER(vp)]),
         "bldfm_host_free": (C.c_int, [vp]),
         "bldfm_device_alloc": (C.c_int, [C.c_int, i64, C.POINTER(vp)]),

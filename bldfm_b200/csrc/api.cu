@@ -1267,6 +1267,33 @@ int bldfm_march(int device, int64_t M, const double* p0, const double* q0, int32
     return rc;
 }
 
+int bldfm_march_coverage(const bldfm_geometry* g, int32_t row0, int32_t rows, int32_t half_plane, int32_t* count,
+                         int64_t* nthreads)
+{
+    if (!g || !count || !nthreads) return fail(BLDFM_ERR_INVALID, "NULL argument");
+    if (rows < 0 || row0 < 0 || row0 + rows > (half_plane ? g->nly / 2 + 1 : g->nly))
+        return fail(BLDFM_ERR_INVALID, "row range outside the marched rows");
+    MarchArgs a{};
+    a.nlx = g->nlx; a.nly = g->nly; a.ky0 = row0; a.nrows = rows; a.herm = half_plane ? 1 : 0;
+    a.nly_loc = half_plane ? g->nly : rows;
+    const int64_t n = march_thread_count(g->nlx, g->nly, row0, rows, half_plane != 0);
+    *nthreads = n;
+    ModeMap m;
+    // one more than the launch covers: the map must reject it
+    for (int64_t tid = 0; tid <= n; ++tid) {
+        if (!march_map(a, tid, m)) {
+            if (tid < n) return fail(BLDFM_ERR_INVALID, "thread map rejects a thread of the launch");
+            continue;
+        }
+        if (tid == n) return fail(BLDFM_ERR_INVALID, "thread map accepts a thread beyond the launch");
+        // full-plane launches index their own rows; report them in the full [nly][nlx] layout as well
+        const int64_t mode = half_plane ? m.mode : (int64_t)m.ky * g->nlx + m.kx;
+        count[mode] += 1;
+        if (m.mirror >= 0) count[m.mirror] += 1;
+    }
+    return BLDFM_OK;
+}
+
 int bldfm_host_alloc(int64_t bytes, void** out)
 {
     if (!out || bytes < 0) return fail(BLDFM_ERR_INVALID, "bad argument");

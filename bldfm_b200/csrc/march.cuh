@@ -265,7 +265,7 @@ __host__ __device__ __forceinline__ int64_t march_thread_count(int nlx, int nly,
     return (int64_t)nlx * rows + n_extra;
 }
 
-__device__ __forceinline__ bool march_map(const MarchArgs& a, int64_t tid, ModeMap& m)
+__host__ __device__ __forceinline__ bool march_map(const MarchArgs& a, int64_t tid, ModeMap& m)
 {
     const int64_t nmain = (int64_t)a.nlx * a.nrows;
     if (!a.herm) {

@@ -189,6 +189,14 @@ int  bldfm_march(int device, int64_t M, const double *p0, const double *q0, int3
                  const double *Lx, const double *Ly, int flags,
                  double *p_top, double *q_top, double *P, double *Q);
 
+/* Test hook for the thread -> Fourier-mode map of the march kernel (bldfm_b200/csrc/march.cuh), evaluated on
+ * the host: for a launch over the rows [row0, row0+rows) -- of the half-plane ky <= nly/2 when half_plane != 0,
+ * of all nly rows otherwise -- adds 1 to count[ky*nlx + kx] (host, [nly][nlx] int32, caller-zeroed) for every mode
+ * the launch writes, directly or as the conjugate mirror; *nthreads = threads of the launch.  The modes of
+ * ivp_solver (src/bldfm/solver.py:158-162,221) must each be written exactly once. */
+int  bldfm_march_coverage(const bldfm_geometry *g, int32_t row0, int32_t rows, int32_t half_plane, int32_t *count,
+                          int64_t *nthreads);
+
 /* ---- memory helpers (so that callers need no other CUDA binding) */
 int  bldfm_host_alloc(int64_t bytes, void **out);      /* pinned host memory */
 int  bldfm_host_free(void *p);

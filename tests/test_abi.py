@@ -82,3 +82,41 @@ def test_product_never_imports_oracle():
         assert "oracle" not in f.read_text(), f
     for f in list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
         assert "oracle" not in f.read_text(), f
+
+
+@pytest.mark.parametrize("shape,modes,halo", [
+    ((512, 512), (512, 512), None), ((32, 48), (48, 32), 0.0), ((24, 40), (16, 8), 35.0), ((2, 2), (2, 2), None),
+    ((15, 45), (512, 512), 0.0), ((33, 20), (512, 512), 0.0), ((20, 33), (512, 512), 0.0), ((100, 100), (50, 66), None),
+])
+def test_march_thread_map_covers_every_mode_once(L, shape, modes, halo):
+    """Half-plane march (csrc/march.cuh): rows ky <= nly/2 plus the mirror stores plus the extra Nyquist-column
+    threads must write each retained mode exactly once -- in one launch, and split in row blocks like the
+    sharded solve does; the full-plane map is the identity."""
+    g = L.geometry(shape, (shape[1] * 7.0, shape[0] * 7.0), modes, halo)
+    lib = L.lib()
+    nth = C.c_int64(0)
+
+    def cover(row0, rows, half, count):
+        L.check(lib.bldfm_march_coverage(C.byref(g), row0, rows, half, count.ctypes.data_as(C.c_void_p), C.byref(nth)))
+        return nth.value
+
+    nrow = g.nly // 2 + 1
+    count = np.zeros((g.nly, g.nlx), np.int32)
+    n = cover(0, nrow, 1, count)
+    assert (count == 1).all()
+    # about half the modes are marched (the reference marches all of them)
+    assert n == g.nlx * nrow + ((g.nly - 1) // 2 if g.nlx % 2 == 0 else 0)
+    for G in (2, 3, 8):
+        rp = -(-nrow // G)
+        if (G - 1) * rp >= nrow:
+            continue
+        count = np.zeros((g.nly, g.nlx), np.int32)
+        total = 0
+        for r in range(G):
+            total += cover(r * rp, min(rp, nrow - r * rp), 1, count)
+        assert (count == 1).all(), G
+        assert total == n
+    count = np.zeros((g.nly, g.nlx), np.int32)
+    assert cover(0, g.nly, 0, count) == g.nlx * g.nly and (count == 1).all()
+    with pytest.raises(ValueError):
+        cover(0, nrow + 1, 1, count)

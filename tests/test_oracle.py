@@ -123,3 +123,32 @@ def test_cache_put_get_clear(tmp_path):
     assert c.get(z, profs, (10.0, 20.0), (8, 8), (1.0, 2.5), None, "single") is None
     c.clear()
     assert c.get(*args) is None
+
+
+@pytest.mark.parametrize("shape,modes", [((48, 64), (64, 48)), ((24, 40), (16, 8)), ((15, 45), (512, 512))])
+def test_reference_spectra_are_conjugate_symmetric(oracle, shape, modes):
+    """The property the half-plane march of the CUDA path rests on (bldfm_b200/csrc/march.cuh), checked on
+    the CPU restatement of the reference (itself bit-identical to the reference's numba ivp_solver): in
+    footprint mode the combined, shifted spectra satisfy S[-ky][-kx] == conj(S[ky][kx]) BIT FOR BIT for every
+    retained mode whose partner is retained too (everything but the Nyquist row/column of even sizes)."""
+    from bldfm_b200.pbl_model import vertical_profiles
+    ny, nx = shape
+    dom = (nx * 9.0, ny * 11.0)
+    z, prof = vertical_profiles(12, 8.0, (2.5, -3.5), ustar=0.35, mol=-80.0)
+    halo = 0.0 if modes[0] > 100 else None
+    tp, tq = oracle.solve(np.zeros((ny, nx)), z, prof, dom, [0, 7, 12], modes=modes, meas_pt=(dom[0] * 0.4, dom[1] * 0.6),
+                          srf_bg_conc=0.2, footprint=True, halo=halo, precision="double", return_spectral=True)
+    nlv, nly, nlx = tp.shape
+    fx = np.fft.fftfreq(nlx, 1.0 / nlx).astype(int)
+    fy = np.fft.fftfreq(nly, 1.0 / nly).astype(int)
+    ix = {f: i for i, f in enumerate(fx)}
+    iy = {f: i for i, f in enumerate(fy)}
+    checked = 0
+    for ky, f_y in enumerate(fy):
+        for kx, f_x in enumerate(fx):
+            if -f_y in iy and -f_x in ix:
+                my, mx = iy[-f_y], ix[-f_x]
+                assert np.array_equal(tp[:, my, mx], np.conj(tp[:, ky, kx]))
+                assert np.array_equal(tq[:, my, mx], np.conj(tq[:, ky, kx]))
+                checked += 1
+    assert checked >= (nlx - 1) * (nly - 1)
