@@ -178,10 +178,13 @@ def steady_state_transport_solver(
         plan, C.byref(prob), _levels_ptr(lv64), nlv,
         None if src is None else _lib.ptr(src), flags | (_lib.ASYNC if pinned else 0), base, base + conc.nbytes)
     _lib.check(rc)
-    grid = make_grid(z, lv, domain, nx, ny)
-    result = (grid, np.squeeze(conc), np.squeeze(flx))
-    if pinned:
-        _lib.check(L.bldfm_plan_synchronize(plan))
+    try:
+        grid = make_grid(z, lv, domain, nx, ny)
+        result = (grid, np.squeeze(conc), np.squeeze(flx))
+    finally:
+        # never leave with the copy into `both` still in flight: the buffer returns to the pool when dropped
+        if pinned:
+            _lib.check(L.bldfm_plan_synchronize(plan))
     del keep
 
     if cache is not None and footprint:                                    # solver.py:301-302
