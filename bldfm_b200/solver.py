@@ -204,6 +204,7 @@ def solve_batched(srf_flx, zs, profiles_list, domain, levels, modes=(512, 512), 
 
     ``wait=False`` only enqueues the work: the returned arrays (pinned host memory) are valid after
     ``synchronize()``; the device->host copy of this batch then overlaps the kernels of the next one.
+    Keep the returned arrays referenced until then -- a dropped array hands its buffer back to the pool.
     """
     q0 = np.asarray(srf_flx)
     ny, nx = q0.shape
