@@ -1,5 +1,5 @@
-"""Time the other BASELINE configs (1, 3, 4-subsample) on one GPU; parity-spot-check vs the oracle
-where it finishes in seconds.  Prints one JSON line per config.
+"""Time the other BASELINE configs (1, 3, 4-subsample) on one GPU.  Prints one JSON line per config.
+(Parity of these configs against the oracle lives in tests/test_gpu_parity.py.)
 
     python scripts/bench_configs.py [--configs 1,3,4] [--reps 5]
 """
@@ -53,25 +53,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="1,3,4")
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--oracle", action="store_true")
     args = ap.parse_args()
     which = set(args.configs.split(","))
-    O = None
-    if args.oracle:
-        from oracle import bldfm_oracle as O
-        O.build()
 
     if "1" in which:
         for prec in ("single", "double"):
             kw = config1(prec)
             med, best = timeit(lambda: bldfm_b200.steady_state_transport_solver(**kw), args.reps)
             out = {"config": 1, "precision": prec, "e2e_ms_median": med * 1e3, "e2e_ms_min": best * 1e3}
-            if O is not None:
-                _, c, f = bldfm_b200.steady_state_transport_solver(**kw)
-                t0 = time.perf_counter()
-                _, oc, of = O.solve(nthreads=O.max_threads(), **kw)
-                out.update(cpu_port_ms=(time.perf_counter() - t0) * 1e3, rel_l2_conc=rel(c, oc), rel_l2_flx=rel(f, of),
-                           dtype=str(c.dtype))
             print(json.dumps(out), flush=True)
 
     if "3" in which:
@@ -95,12 +84,6 @@ def main():
                "out_bytes": 2 * nlv * 1024 * 1024 * 8, "out_gbs_device": 2 * nlv * 1024 * 1024 * 8 / gpu_ms / 1e6,
                "workspace_gb": bldfm_b200.get_fft_manager().workspace_bytes() / 1e9}
         print(json.dumps(out), flush=True)
-        if O is not None:
-            kws = config3(256, 32)
-            _, c, f = bldfm_b200.steady_state_transport_solver(**kws)
-            _, oc, of = O.solve(nthreads=O.max_threads(), **kws)
-            print(json.dumps({"config": "3 (256x256x33 replica) parity", "rel_l2_conc": rel(c, oc), "rel_l2_flx": rel(f, of)}),
-                  flush=True)
         bldfm_b200.reset_fft_manager()
 
     if "4" in which:

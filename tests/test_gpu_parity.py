@@ -336,3 +336,43 @@ def test_default_halo_passes_equal_generic_passes(B, shape):
         assert rel_l2(f1, f0) <= tol, (case["footprint"], rel_l2(f1, f0))
         assert rel_l2(c2, c0) <= tol, (case["footprint"], rel_l2(c2, c0))
         assert rel_l2(f2, f0) <= tol, (case["footprint"], rel_l2(f2, f0))
+
+
+def test_baseline_config1_minimal_yaml_against_oracle(B, oracle):
+    """BASELINE config 1 = examples/configs/minimal.yaml as shipped (512x256, n=16, domain 2000x1000 m, modes
+    (512,512), default halo -> padded 1536x1280, diamond source, non-footprint, tower at (0,0)): default
+    precision="single" (float32 fields, tolerance 1e-5) and precision="double" (1e-10)."""
+    from bldfm_b200.pbl_model import vertical_profiles
+    from bldfm_b200.utils import compute_wind_fields, ideal_source
+    u, v = compute_wind_fields(4.123, 256.0)
+    z, prof = vertical_profiles(16, 10.0, (u, v), ustar=0.4, mol=1e9)
+    src = ideal_source((512, 256), (2000.0, 1000.0))
+    for precision, tol in (("single", TOL_F32), ("double", TOL_F64)):
+        kw = dict(srf_flx=src, z=z, profiles=prof, domain=(2000.0, 1000.0), levels=16, modes=(512, 512),
+                  meas_pt=(0.0, 0.0), footprint=False, precision=precision)
+        _, c, f = B.steady_state_transport_solver(**kw)
+        _, oc, of = oracle.solve(nthreads=oracle.max_threads(), **kw)
+        assert c.dtype == oc.dtype and c.shape == oc.shape == (256, 512)
+        assert rel_l2(c, oc) <= tol, (precision, rel_l2(c, oc))
+        assert rel_l2(f, of) <= tol, (precision, rel_l2(f, of))
+
+
+def test_baseline_config3_replica_against_oracle(B, oracle):
+    """BASELINE config 3 (3-D plume, all levels to z_m written out) at a size the oracle finishes in seconds:
+    256x256, n=32 -> 33 output levels, neutral MOST, point source, default halo (the fft24 plan with Q = 32)."""
+    from bldfm_b200.pbl_model import vertical_profiles
+    from bldfm_b200.utils import ideal_source
+    n, nz = 256, 32
+    z, prof = vertical_profiles(nz, 10.0, (6.0, 0.0), ustar=0.4)
+    dom = (8000.0 * n / 1024, 8000.0 * n / 1024)
+    src = ideal_source((n, n), dom, src_loc=(dom[0] / 4, dom[1] / 2), shape="point")
+    kw = dict(srf_flx=src, z=z, profiles=prof, domain=dom, levels=np.arange(0, nz + 1), modes=(n, n),
+              meas_pt=(0.0, 0.0), footprint=False, precision="double")
+    _, c, f = B.steady_state_transport_solver(**kw)
+    _, oc, of = oracle.solve(nthreads=oracle.max_threads(), **kw)
+    assert c.shape == oc.shape == (nz + 1, n, n)
+    assert rel_l2(c, oc) <= TOL_F64, rel_l2(c, oc)
+    assert rel_l2(f, of) <= TOL_F64, rel_l2(f, of)
+    # level by level as well (the upper levels carry little mass and would hide in the global norm)
+    for l in range(nz + 1):
+        assert rel_l2(f[l], of[l]) <= 1e-9, (l, rel_l2(f[l], of[l]))
