@@ -82,6 +82,9 @@ def test_product_never_imports_oracle():
         assert "oracle" not in f.read_text(), f
     for f in list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")):
         assert "oracle" not in f.read_text(), f
+    # the measurement scripts time the product only; parity tools live under tests/
+    for f in (ROOT / "scripts").glob("*.py"):
+        assert not re.search(r"^\s*(from|import)\s+oracle", f.read_text(), re.M), f
 
 
 @pytest.mark.parametrize("shape,modes,halo", [
