@@ -36,6 +36,7 @@ ASYNC = 0x040
 FFT_LIBRARY = 0x080
 FFT_FULL = 0x100
 MARCH_FULL = 0x200
+MARCH_AUTO = 0x400
 
 # every symbol include/bldfm_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
@@ -48,6 +49,9 @@ EXPORTS = [
     "bldfm_memcpy_d2h", "bldfm_memcpy_h2d", "bldfm_fp64_peak",
     "bldfm_solve_batched_measure", "bldfm_sharded_stage1", "bldfm_sharded_stage2", "bldfm_ipc_export", "bldfm_ipc_open", "bldfm_ipc_close",
     "bldfm_march_coverage",
+    "bldfm_solve_batched_accumulate", "bldfm_kappa", "bldfm_auto_kappa_limit", "bldfm_plan_last_march_mode",
+    "bldfm_device_memset", "bldfm_host_register", "bldfm_host_unregister",
+    "bldfm_peer_signal", "bldfm_peer_wait", "bldfm_peer_status",
 ]
 
 
@@ -123,7 +127,7 @@ def lib():
         "bldfm_plan_last_timings": (C.c_int, [vp, C.POINTER(Timings)]),
         "bldfm_plan_workspace_bytes": (i64, [vp]),
         "bldfm_solve": (C.c_int, [vp, PP, I64P, i32, vp, C.c_int, vp, vp]),
-        "bldfm_solve_batched": (C.c_int, [vp, i32, PP, I64P, i32, vp, C.c_int, vp, vp]),
+        "bldfm_solve_batched": (C.c_int, [vp, i32, vp, I64P, i32, vp, C.c_int, vp, vp]),
         "bldfm_solve_spectral": (C.c_int, [vp, PP, I64P, i32, vp, C.c_int, vp, vp]),
         "bldfm_march": (C.c_int, [C.c_int, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, I64P,
                                   vp, vp, C.c_int, vp, vp, vp, vp]),
@@ -135,12 +139,22 @@ def lib():
         "bldfm_memcpy_d2h": (C.c_int, [C.c_int, vp, vp, i64]),
         "bldfm_memcpy_h2d": (C.c_int, [C.c_int, vp, vp, i64]),
         "bldfm_fp64_peak": (C.c_int, [C.c_int, C.c_int, C.c_int, _DP]),
-        "bldfm_solve_batched_measure": (C.c_int, [vp, i32, PP, I64P, i32, vp, C.c_int, vp, vp, vp]),
+        "bldfm_solve_batched_measure": (C.c_int, [vp, i32, vp, I64P, i32, vp, C.c_int, vp, vp, vp]),
         "bldfm_sharded_stage1": (C.c_int, [vp, PP, I64P, i32, vp, C.c_int, i32, i32, vp, vp, vp, vp]),
         "bldfm_sharded_stage2": (C.c_int, [vp, i32, C.c_int, i32, i32, vp, vp, vp, vp]),
         "bldfm_ipc_export": (C.c_int, [vp, C.c_char_p]),
         "bldfm_ipc_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(vp)]),
         "bldfm_ipc_close": (C.c_int, [C.c_int, vp]),
+        "bldfm_solve_batched_accumulate": (C.c_int, [vp, i32, vp, I64P, i32, vp, C.c_int, vp, i32, vp, vp]),
+        "bldfm_kappa": (C.c_int, [GP, PP, i32, _DP]),
+        "bldfm_auto_kappa_limit": (dbl, []),
+        "bldfm_plan_last_march_mode": (C.c_int, [vp]),
+        "bldfm_device_memset": (C.c_int, [C.c_int, vp, C.c_int, i64]),
+        "bldfm_host_register": (C.c_int, [vp, i64]),
+        "bldfm_host_unregister": (C.c_int, [vp]),
+        "bldfm_peer_signal": (C.c_int, [vp, vp, i32, C.c_uint64]),
+        "bldfm_peer_wait": (C.c_int, [vp, vp, i32, C.c_uint64, dbl]),
+        "bldfm_peer_status": (C.c_int, [vp, C.POINTER(i32)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -226,3 +240,32 @@ def make_problem(z, profiles, meas_pt, srf_bg_conc):
     p = Problem(base, base + row, base + 2 * row, base + 3 * row, base + 4 * row, base + 5 * row, n, 0,
                 float(meas_pt[0]), float(meas_pt[1]), float(srf_bg_conc))
     return p, buf
+
+
+PROBLEM_DTYPE = np.dtype([("z", "<u8"), ("u", "<u8"), ("v", "<u8"), ("Kx", "<u8"), ("Ky", "<u8"), ("Kz", "<u8"),
+                          ("nz", "<i4"), ("reserved", "<i4"), ("xm", "<f8"), ("ym", "<f8"), ("srf_bg_conc", "<f8")])
+assert PROBLEM_DTYPE.itemsize == C.sizeof(Problem)
+
+
+def problems_from_batch(batch, row_of_problem, xm, ym, srf_bg_conc=0.0):
+    """``bldfm_problem[P]`` built without a Python loop: problem p uses row ``row_of_problem[p]`` of a
+    ``pbl_model.ProfileBatch`` (``[B, 6, nzmax]`` buffer) and the measurement point ``(xm[p], ym[p])``.
+
+    Returns ``(array, keepalive)``: a numpy structured array with the layout of ``Problem`` (pass
+    ``array.ctypes.data`` as the ``bldfm_problem*``) and the objects that must stay referenced during the call.
+    """
+    buf = batch.buf
+    if buf.dtype != np.float64 or not buf.flags.c_contiguous:
+        raise ValueError("profile batch must be a C-contiguous float64 [B, 6, nzmax] buffer")
+    rows = np.asarray(row_of_problem, dtype=np.int64)
+    P = rows.shape[0]
+    nzmax = buf.shape[2]
+    base = buf.ctypes.data + rows.astype(np.uint64) * np.uint64(6 * nzmax * 8)
+    arr = np.zeros(P, dtype=PROBLEM_DTYPE)
+    for k, name in enumerate(("z", "u", "v", "Kx", "Ky", "Kz")):
+        arr[name] = base + np.uint64(k * nzmax * 8)
+    arr["nz"] = np.asarray(batch.nz, dtype=np.int64)[rows]
+    arr["xm"] = xm
+    arr["ym"] = ym
+    arr["srf_bg_conc"] = srf_bg_conc
+    return arr, (buf, arr)

@@ -125,12 +125,13 @@ struct bldfm_plan {
     cudaEvent_t compute_done = nullptr;
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
     bool copy_pending[2] = {false, false};
-    uint64_t weight_sig = 0;                  // signature of the weight map held in `weight`
     DevBuf weight, partial;  // f-4 weighted sums: weight map [ny][nx], partial sums | results
+    DevBuf peer_status;      // fused transpose: set by k_peer_wait when a peer never arrived
     Staging staging[kStagingSlots];
     int staging_next = 0;
     std::map<uint64_t, cufftHandle> fft_plans;
     int64_t launches = 0;
+    int last_march_fma = 0;                   // arithmetic mode the most recent march ran in (BLDFM_MARCH_AUTO)
     bool profiling = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_recorded = false;
@@ -218,6 +219,35 @@ bool same_march(const bldfm_problem& a, const bldfm_problem& b)
     return !memcmp(a.z, b.z, nb) && !memcmp(a.u, b.u, nb) && !memcmp(a.v, b.v, nb) &&
            !memcmp(a.Kx, b.Kx, nb) && !memcmp(a.Ky, b.Ky, nb) && !memcmp(a.Kz, b.Kz, nb) &&
            !memcmp(&a.srf_bg_conc, &b.srf_bg_conc, sizeof(double));
+}
+
+// Conditioning number kappa(z_level) of linear shooting: growth exponent of the two
+// auxiliary IVP solutions at the largest retained wavenumbers, summed over the steps below `level`.
+double march_kappa(const bldfm_problem& pb, const bldfm_geometry& g, int level)
+{
+    const double lx = 2.0 * M_PI / (g.dx * g.nxe) * (g.nlx / 2.0);
+    const double ly = 2.0 * M_PI / (g.dy * g.nye) * (g.nly / 2.0);
+    const int top = std::min(level, pb.nz - 1);
+    double k = 0.0;
+    for (int i = 0; i < top; ++i) {
+        const double re = (pb.Kx[i] * lx * lx + pb.Ky[i] * ly * ly) / pb.Kz[i];
+        const double im = (std::fabs(pb.u[i]) * lx + std::fabs(pb.v[i]) * ly) / pb.Kz[i];
+        const double mod = std::hypot(re, im);
+        k += std::sqrt(0.5 * (mod + re)) * (pb.z[i + 1] - pb.z[i]);          // Re sqrt(re + i*im), re >= 0
+    }
+    return k;
+}
+
+// kappa up to which BLDFM_MARCH_AUTO picks the FMA-contracted march.  The FMA march differs from the reference
+// at the reference's own round-off noise level, measured as ~10^(0.468*kappa - 15.2) rel-L2 for the flux
+// footprint; 8.5 keeps the prediction below 1e-11, a decade under the 1e-10 parity bar.
+double auto_kappa_limit()
+{
+    static const double v = [] {
+        const char* e = std::getenv("BLDFM_B200_AUTO_KAPPA");
+        return (e && *e) ? std::atof(e) : 8.5;
+    }();
+    return v;
 }
 
 int grid_for(int64_t n, int threads, int num_sms)
@@ -396,7 +426,6 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     const bool footprint = flags & BLDFM_FOOTPRINT;
     const bool analytic = flags & BLDFM_ANALYTIC;
     const bool dbl = flags & BLDFM_DOUBLE;
-    const bool fma_mode = flags & BLDFM_MARCH_FMA;
     const bool out_dev = flags & BLDFM_OUT_ON_DEVICE;
     const bool spectral = out.tfftp != nullptr;
     if (!footprint && !srf_flx) return fail(BLDFM_ERR_INVALID, "srf_flx is NULL in non-footprint mode");
@@ -422,7 +451,9 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
             const int Rp = herm_shard_rows(g, sh->nranks);
             ky0 = sh->rank * Rp;
             rows = std::min(Rp, g.nly / 2 + 1 - ky0);
-            if (rows < 1) return fail(BLDFM_ERR_INVALID, "sharded solve: more ranks than row blocks of the half-plane");
+            // more ranks than row blocks: this rank owns no rows (its block of the receive buffers lies beyond
+            // row nly/2 and is never read by stage 2)
+            if (rows < 1) return BLDFM_OK;
         } else {
             rows = g.nly / sh->nranks;
             ky0 = sh->rank * rows;
@@ -465,6 +496,15 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     }
     const int ngroups = (int)rep.size();
     const int coef_stride = nz_max - 1;
+    // BLDFM_MARCH_AUTO: the FMA-contracted march where every march of the batch is well conditioned
+    bool fma_mode = (flags & BLDFM_MARCH_FMA) != 0;
+    if (!fma_mode && (flags & BLDFM_MARCH_AUTO) && !analytic) {
+        fma_mode = true;
+        const int lvl = lp.last_level >= 0 ? lp.last_level : nz_max - 1;
+        for (int gi = 0; gi < ngroups && fma_mode; ++gi)
+            if (!(march_kappa(probs[rep[(size_t)gi]], g, lvl) <= auto_kappa_limit())) fma_mode = false;
+    }
+    pl->last_march_fma = fma_mode ? 1 : 0;
 
     // ---- shifts and output dtype
     std::vector<TowerDesc> towers((size_t)nprob);
@@ -822,6 +862,37 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     return BLDFM_OK;
 }
 
+// ---- device-side synchronisation of the fused (peer-store) transpose ---------------------------------
+// Rank r, after its pass X has stored into the peers' receive buffers, publishes the solve's sequence number
+// in slot r of every peer's flag array (system-scope release); before pass Y it waits until all G slots of
+// its own array carry that number (system-scope acquire).  No host thread and no collective is involved.
+__global__ void k_peer_signal(unsigned long long* const* __restrict__ peer_slots, int n, unsigned long long value)
+{
+    const int i = threadIdx.x;
+    if (i < n) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(peer_slots[i]), "l"(value) : "memory");
+    }
+}
+
+__global__ void k_peer_wait(const unsigned long long* __restrict__ flags, int n, unsigned long long value,
+                            int* __restrict__ status, unsigned long long timeout_ns)
+{
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + i) : "memory");
+        if (v >= value) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) { atomicExch(status, 1 + i); break; }   // a peer never arrived: report, do not hang
+        __nanosleep(200);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 k_fp64_peak(double* out, int iters, int use_fma, double seed)
 {
@@ -976,7 +1047,7 @@ int bldfm_plan_destroy(bldfm_plan* pl)
     if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
     pl->tables.release(); pl->params.release(); pl->spec_p.release(); pl->spec_q.release();
     pl->pad_in.release(); pl->pad_out.release(); pl->src_in.release(); pl->src_pad.release();
-    pl->weight.release(); pl->partial.release();
+    pl->weight.release(); pl->partial.release(); pl->peer_status.release();
     pl->fft_work.release(); pl->tw64.release(); pl->tw32.release(); pl->t24_64.release(); pl->t24_32.release(); pl->t48_64.release(); pl->t48_32.release(); pl->out_c.release(); pl->out_f.release();
     for (auto& s : pl->staging) {
         if (s.host) cudaFreeHost(s.host);
@@ -1073,17 +1144,16 @@ int bldfm_solve_batched_measure(bldfm_plan* pl, int32_t nprob, const bldfm_probl
     TRY(pl->out_f.ensure((size_t)nfields * per_field * relem));
     TRY(pl->weight.ensure((size_t)per_field * sizeof(double)));
     TRY(pl->partial.ensure((size_t)2 * nfields * (kReduceBlocks + 1) * sizeof(double)));
+    // the weight map is uploaded on every call (2 MB at 512^2: ~40 us of H2D against a batch of solves); a
+    // caller that edits its map in place must never see stale device weights.  The copy is staged through
+    // the plan's pinned ring so that the caller's (pageable) array can change right after the call returns.
     {
-        // upload the weight map only when it changed: signature = pointer, size and 1024 samples
-        uint64_t sig = fnv1a(&weight, sizeof(weight), 1469598103934665603ull);
-        sig = fnv1a(&per_field, sizeof(per_field), sig);
-        const int64_t stride = std::max<int64_t>(1, per_field / 1024);
-        for (int64_t i = 0; i < per_field; i += stride) sig = fnv1a(weight + i, sizeof(double), sig);
-        sig = fnv1a(weight + per_field - 1, sizeof(double), sig);
-        if (sig != pl->weight_sig) {
-            CUDA_TRY(cudaMemcpyAsync(pl->weight.p, weight, (size_t)per_field * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
-            pl->weight_sig = sig;
-        }
+        Staging* wst = nullptr;
+        TRY(acquire_staging(pl, (size_t)per_field * sizeof(double), &wst));
+        memcpy(wst->host, weight, (size_t)per_field * sizeof(double));
+        CUDA_TRY(cudaMemcpyAsync(pl->weight.p, wst->host, (size_t)per_field * sizeof(double), cudaMemcpyHostToDevice, pl->stream));
+        CUDA_TRY(cudaEventRecord(wst->done, pl->stream));
+        wst->in_flight = true;
     }
     for (int k = 0; k < 2; ++k)
         if (pl->copy_pending[k]) { CUDA_TRY(cudaStreamWaitEvent(pl->stream, pl->copy_done[k], 0)); }
@@ -1108,6 +1178,88 @@ int bldfm_solve_batched_measure(bldfm_plan* pl, int32_t nprob, const bldfm_probl
     // BLDFM_ASYNC: conc_w / flx_w must be pinned and are valid after bldfm_plan_synchronize(); the next
     // batch (same stream, so its kernels are ordered after these copies) can be enqueued meanwhile
     if (!(flags & BLDFM_ASYNC)) CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return BLDFM_OK;
+}
+
+int bldfm_solve_batched_accumulate(bldfm_plan* pl, int32_t nprob, const bldfm_problem* probs,
+                                   const int64_t* levels, int32_t nlv, const double* srf_flx, int flags,
+                                   const int32_t* slot_of, int32_t nslots, double* acc_conc, double* acc_flx)
+{
+    if (!pl || !slot_of || !acc_conc || !acc_flx) return fail(BLDFM_ERR_INVALID, "NULL argument");
+    if (nprob < 1 || nlv < 1 || nslots < 1) return fail(BLDFM_ERR_INVALID, "bad sizes");
+    const bldfm_geometry& g = pl->g;
+    DeviceGuard guard(pl->device);
+    if (!guard.ok) return fail(BLDFM_ERR_CUDA, "cudaSetDevice failed");
+    for (int b = 0; b < nprob; ++b)
+        if (slot_of[b] >= nslots) return fail(BLDFM_ERR_INVALID, "slot_of entry out of range");
+    const int64_t per = (int64_t)nlv * g.nx * g.ny;
+    bool any_shift = false;
+    for (int b = 0; b < nprob; ++b)
+        any_shift |= (flags & BLDFM_FOOTPRINT) || (probs[b].xm * probs[b].xm + probs[b].ym * probs[b].ym > 0.0);
+    const bool f32 = !(flags & BLDFM_DOUBLE) && !any_shift;
+    const size_t relem = f32 ? sizeof(float) : sizeof(double);
+    TRY(pl->out_c.ensure((size_t)nprob * per * relem));
+    TRY(pl->out_f.ensure((size_t)nprob * per * relem));
+    for (int k = 0; k < 2; ++k)
+        if (pl->copy_pending[k]) { CUDA_TRY(cudaStreamWaitEvent(pl->stream, pl->copy_done[k], 0)); }
+    SolveOut o; o.conc = pl->out_c.p; o.flx = pl->out_f.p;
+    TRY(solve_impl(pl, nprob, probs, levels, nlv, srf_flx, flags | BLDFM_OUT_ON_DEVICE | BLDFM_ASYNC, o));
+    // slot table rides in the pinned staging ring
+    Staging* st = nullptr;
+    TRY(acquire_staging(pl, sizeof(int32_t) * (size_t)nprob, &st));
+    memcpy(st->host, slot_of, sizeof(int32_t) * (size_t)nprob);
+    TRY(pl->partial.ensure(sizeof(int32_t) * (size_t)nprob));
+    CUDA_TRY(cudaMemcpyAsync(pl->partial.p, st->host, sizeof(int32_t) * (size_t)nprob, cudaMemcpyHostToDevice, pl->stream));
+    CUDA_TRY(cudaEventRecord(st->done, pl->stream));
+    st->in_flight = true;
+    const dim3 grid((unsigned)std::min<int64_t>((per + 255) / 256, (int64_t)pl->num_sms * 4), (unsigned)nslots);
+    const int32_t* d_slot = static_cast<const int32_t*>(pl->partial.p);
+    if (f32) {
+        k_accumulate<float><<<grid, 256, 0, pl->stream>>>(static_cast<const float*>(pl->out_c.p), acc_conc, d_slot, nprob, per);
+        k_accumulate<float><<<grid, 256, 0, pl->stream>>>(static_cast<const float*>(pl->out_f.p), acc_flx, d_slot, nprob, per);
+    } else {
+        k_accumulate<double><<<grid, 256, 0, pl->stream>>>(static_cast<const double*>(pl->out_c.p), acc_conc, d_slot, nprob, per);
+        k_accumulate<double><<<grid, 256, 0, pl->stream>>>(static_cast<const double*>(pl->out_f.p), acc_flx, d_slot, nprob, per);
+    }
+    CUDA_TRY(cudaGetLastError());
+    pl->launches += 2;
+    if (!(flags & BLDFM_ASYNC)) CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return BLDFM_OK;
+}
+
+int bldfm_kappa(const bldfm_geometry* g, const bldfm_problem* prob, int32_t level, double* kappa)
+{
+    if (!g || !prob || !kappa) return fail(BLDFM_ERR_INVALID, "NULL argument");
+    if (prob->nz < 2 || !prob->z || !prob->u || !prob->v || !prob->Kx || !prob->Ky || !prob->Kz)
+        return fail(BLDFM_ERR_INVALID, "need nz >= 2 and all profiles");
+    int lvl = level < 0 ? level + prob->nz : level;
+    if (lvl < 0 || lvl >= prob->nz) return fail(BLDFM_ERR_LEVEL_RANGE, "level out of range");
+    *kappa = march_kappa(*prob, *g, lvl);
+    return BLDFM_OK;
+}
+
+double bldfm_auto_kappa_limit(void) { return auto_kappa_limit(); }
+
+int bldfm_plan_last_march_mode(const bldfm_plan* pl) { return pl ? pl->last_march_fma : 0; }
+
+int bldfm_host_register(void* p, int64_t bytes)
+{
+    if (!p || bytes <= 0) return fail(BLDFM_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable));
+    return BLDFM_OK;
+}
+
+int bldfm_host_unregister(void* p)
+{
+    if (p) CUDA_TRY(cudaHostUnregister(p));
+    return BLDFM_OK;
+}
+
+int bldfm_device_memset(int device, void* p, int value, int64_t bytes)
+{
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(BLDFM_ERR_CUDA, "cudaSetDevice failed");
+    CUDA_TRY(cudaMemset(p, value, (size_t)bytes));
     return BLDFM_OK;
 }
 
@@ -1154,6 +1306,47 @@ int bldfm_sharded_stage2(bldfm_plan* pl, int32_t nlv, int flags, int32_t rank, i
     if (fe != cudaSuccess) return fail(BLDFM_ERR_CUDA, std::string("sharded y-pass: ") + cudaGetErrorString(fe));
     pl->launches += nl;
     if (!(flags & BLDFM_ASYNC)) CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return BLDFM_OK;
+}
+
+int bldfm_peer_signal(bldfm_plan* pl, void* const* peer_slots, int32_t nranks, uint64_t value)
+{
+    if (!pl || !peer_slots || nranks < 1 || nranks > 32) return fail(BLDFM_ERR_INVALID, "bad argument");
+    DeviceGuard guard(pl->device);
+    if (!guard.ok) return fail(BLDFM_ERR_CUDA, "cudaSetDevice failed");
+    k_peer_signal<<<1, 32, 0, pl->stream>>>(reinterpret_cast<unsigned long long* const*>(peer_slots), nranks,
+                                            (unsigned long long)value);
+    CUDA_TRY(cudaGetLastError());
+    pl->launches++;
+    return BLDFM_OK;
+}
+
+int bldfm_peer_wait(bldfm_plan* pl, const void* flags, int32_t nranks, uint64_t value, double timeout_s)
+{
+    if (!pl || !flags || nranks < 1 || nranks > 32) return fail(BLDFM_ERR_INVALID, "bad argument");
+    DeviceGuard guard(pl->device);
+    if (!guard.ok) return fail(BLDFM_ERR_CUDA, "cudaSetDevice failed");
+    bool grew = false;
+    TRY(pl->peer_status.ensure(sizeof(int), &grew));
+    if (grew) CUDA_TRY(cudaMemsetAsync(pl->peer_status.p, 0, sizeof(int), pl->stream));
+    const double t = timeout_s > 0.0 ? timeout_s : 20.0;
+    k_peer_wait<<<1, 32, 0, pl->stream>>>(static_cast<const unsigned long long*>(flags), nranks,
+                                          (unsigned long long)value, static_cast<int*>(pl->peer_status.p),
+                                          (unsigned long long)(t * 1e9));
+    CUDA_TRY(cudaGetLastError());
+    pl->launches++;
+    return BLDFM_OK;
+}
+
+int bldfm_peer_status(bldfm_plan* pl, int32_t* status)
+{
+    if (!pl || !status) return fail(BLDFM_ERR_INVALID, "NULL argument");
+    *status = 0;
+    if (!pl->peer_status.p) return BLDFM_OK;
+    DeviceGuard guard(pl->device);
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    CUDA_TRY(cudaMemcpy(status, pl->peer_status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (*status) CUDA_TRY(cudaMemset(pl->peer_status.p, 0, sizeof(int)));
     return BLDFM_OK;
 }
 

@@ -105,4 +105,24 @@ k_weighted_final(const double* __restrict__ partial, double* __restrict__ out, i
     out[f] = acc;
 }
 
+// f-4: time aggregation (examples/timeseries_example.py:46, np.mean over the timesteps of one tower):
+// acc[slot_of[b]] += field[b] for the problems b of one batch, in problem order (deterministic; with the
+// timesteps batched in order this is the summation order of np.add.reduce along axis 0).
+// fields [nprob][per] (per = nlv*ny*nx), acc [nslots][per] float64, slot_of[b] < 0: problem not accumulated.
+template <typename R>
+__global__ void __launch_bounds__(256)
+k_accumulate(const R* __restrict__ fields, double* __restrict__ acc, const int32_t* __restrict__ slot_of,
+             int nprob, int64_t per)
+{
+    const int slot = blockIdx.y;
+    double* dst = acc + (size_t)slot * per;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double a = dst[i];
+        for (int b = 0; b < nprob; ++b)
+            if (slot_of[b] == slot) a += (double)fields[(size_t)b * per + i];
+        dst[i] = a;
+    }
+}
+
 }  // namespace bldfm

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 from . import _lib
 from . import config
@@ -39,13 +40,15 @@ class PlanManager:
             self._forget_memos()
             self._pid = os.getpid()
         dev = config.DEVICE if device is None else int(device)
+        # a bldfm_plan is not thread-safe (include/bldfm_b200.h): every host thread gets its own
+        tid = threading.get_ident()
         # fast path: the handle is remembered on the (cached) Geometry object itself
         memo = geom.__dict__.get("_plans")
         if memo is not None:
-            hit = memo.get((id(self), dev))
+            hit = memo.get((id(self), dev, tid))
             if hit is not None:
                 return hit
-        key = (dev,) + geom.key()
+        key = (dev, tid) + geom.key()
         h = self._plans.get(key)
         if h is not None:
             self._plans[key] = self._plans.pop(key)        # most recently used goes last
@@ -54,7 +57,7 @@ class PlanManager:
             h = C.c_void_p()
             _lib.check(_lib.lib().bldfm_plan_create(C.byref(geom), dev, C.byref(h)))
             self._plans[key] = h
-        geom.__dict__.setdefault("_plans", {})[(id(self), dev)] = h
+        geom.__dict__.setdefault("_plans", {})[(id(self), dev, tid)] = h
         self._memo_owners.append(geom)
         return h
 

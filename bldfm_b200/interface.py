@@ -4,10 +4,15 @@
 The reference runs one Python-level solve per (tower, timestep) -- serially (``run_bldfm_timeseries``,
 ``run_bldfm_multitower``) or fanned out over a process pool (``run_bldfm_parallel``).  Here all
 tasks of a call are grouped, the vertical march is computed once per (measurement height, met step)
-and shared by the towers, chunks of problems go to ``bldfm_solve_batched`` in one
-launch each, and under ``torchrun`` the march groups are spread over the GPUs of the node with a
-single final gather (``distributed.py``).  ``config`` may be the reference's own ``BLDFMConfig`` or
+and shared by the towers, the profiles of all met steps come from ONE vectorised
+``vertical_profiles_batch`` call, chunks of problems go to ``bldfm_solve_batched`` in one launch each,
+and under ``torchrun`` the march groups are spread over the GPUs of the node with a single final
+gather (``distributed.py``).  ``config`` may be the reference's own ``BLDFMConfig`` or
 ``bldfm_b200.schema.Config``.
+
+Beyond the reference's drivers: ``run_bldfm_measure`` (tower fluxes ``sum(footprint * flux_map)``,
+utils.py:80-92) and ``run_bldfm_aggregate`` (time-mean footprint per tower,
+examples/timeseries_example.py:46) reduce on the device and move only the reduced result.
 """
 
 from __future__ import annotations
@@ -17,9 +22,11 @@ from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 
+from . import _lib
 from . import distributed as _dist
-from .pbl_model import vertical_profiles
-from .solver import make_grid, solve_batched, steady_state_transport_solver, synchronize
+from .pbl_model import ProfileBatch, compute_wind_fields_batch, vertical_profiles, vertical_profiles_batch
+from .solver import (FieldAccumulator, make_grid, measure_batched, solve_batched, steady_state_transport_solver,
+                     synchronize)
 from .utils import compute_wind_fields, ideal_source
 
 logger = logging.getLogger("bldfm.interface")
@@ -47,6 +54,25 @@ def _profiles_for(config, z_m, met_step):
     else:
         kw["ustar"] = met_step["ustar"]
     return vertical_profiles(**kw)
+
+
+def profiles_batch(config, z_ms: Sequence[float], met_steps: Sequence[dict]) -> ProfileBatch:
+    """Steps 1+2 (interface.py:73-95) for B (measurement height, met step) pairs in one vectorised pass;
+    row b is bitwise what ``_profiles_for(config, z_ms[b], met_steps[b])`` returns."""
+    ws = np.array([s["wind_speed"] for s in met_steps], dtype=np.float64)
+    wd = np.array([s["wind_dir"] for s in met_steps], dtype=np.float64)
+    mol = np.array([s["mol"] for s in met_steps], dtype=np.float64)
+    um, vm = compute_wind_fields_batch(ws, wd)
+    kw = dict(n=config.domain.nz, meas_height=np.asarray(z_ms, dtype=np.float64), wind=(um, vm), mol=mol,
+              closure=config.solver.closure)
+    z0s = [s.get("z0") for s in met_steps]
+    if all(v is not None for v in z0s):         # z0 takes precedence over ustar (interface.py:77-95)
+        kw["z0"] = np.array(z0s, dtype=np.float64)
+    elif all(v is None for v in z0s):
+        kw["ustar"] = np.array([s["ustar"] for s in met_steps], dtype=np.float64)
+    else:
+        raise ValueError("met steps must either all carry z0 or none")
+    return vertical_profiles_batch(**kw)
 
 
 def _levels(config):
@@ -95,82 +121,147 @@ def run_bldfm_single(config, tower, met_index: int = 0, surface_flux=None, cache
 # batched core
 # ------------------------------------------------------------------------------------------------
 
-def plan_tasks(config, tasks: Sequence[Tuple[int, int]]):
-    """Group tasks (tower index, met index) by march key (z_m, met index).
+def _as_task(config, task):
+    """(tower object, met index) from either (tower index, met index) or (tower object, met index)."""
+    t, mi = task
+    if isinstance(t, (int, np.integer)):
+        t = config.towers[int(t)]
+    return t, int(mi)
+
+
+def plan_tasks(config, tasks: Sequence[Tuple[object, int]]):
+    """Group tasks (tower | tower index, met index) by march key (z_m, met index).
 
     Returns (group_keys, task_group) with task_group[t] = index into group_keys.
     """
     keys: Dict[Tuple[float, int], int] = {}
     task_group = []
-    for ti, mi in tasks:
-        k = (float(config.towers[ti].z_m), int(mi))
+    for task in tasks:
+        tower, mi = _as_task(config, task)
+        k = (float(tower.z_m), mi)
         task_group.append(keys.setdefault(k, len(keys)))
     return list(keys.keys()), task_group
 
 
-def solve_tasks(config, tasks: Sequence[Tuple[int, int]], surface_flux=None, cache=None) -> List[dict]:
-    """Solve the given (tower index, met index) tasks on this process's GPU, batched."""
-    dom, sol = config.domain, config.solver
-    domain = (dom.xmax, dom.ymax)
-    levels = _levels(config)
-    lv = np.array([levels]) if np.ndim(levels) == 0 else np.asarray(levels)
-    srf = _surface_flux(config, surface_flux)
-    results: List[dict] = [None] * len(tasks)
+class TaskBatch:
+    """The pending tasks of one call, prepared for the device without per-task Python work: one
+    ``ProfileBatch`` row per march group, one ``bldfm_problem`` per task, chunk boundaries on group edges."""
 
-    prof_cache: Dict[Tuple[float, int], tuple] = {}
+    def __init__(self, config, tasks):
+        self.config = config
+        self.tasks = [_as_task(config, t) for t in tasks]
+        self.keys, self.task_group = plan_tasks(config, self.tasks)
+        self.steps = {}
+        for _, mi in self.keys:
+            if mi not in self.steps:
+                self.steps[mi] = config.met.get_step(mi)
+        self.profiles = profiles_batch(config, [k[0] for k in self.keys], [self.steps[k[1]] for k in self.keys]) \
+            if self.keys else None
+        dom, sol = config.domain, config.solver
+        self.domain = (dom.xmax, dom.ymax)
+        self.levels = _levels(config)
+        self.lv = np.array([self.levels]) if np.ndim(self.levels) == 0 else np.asarray(self.levels)
+        self.nlv = len(self.lv)
+        self.solver_kw = dict(domain=self.domain, levels=self.levels, modes=dom.modes, footprint=sol.footprint,
+                              analytic=sol.analytic, halo=dom.halo, precision=sol.precision)
+
+    def problems(self, idx):
+        """bldfm_problem array (+ keepalive) for the tasks ``idx`` (indices into self.tasks)."""
+        xm = np.array([self.tasks[t][0].x for t in idx], dtype=np.float64)
+        ym = np.array([self.tasks[t][0].y for t in idx], dtype=np.float64)
+        rows = np.array([self.task_group[t] for t in idx], dtype=np.int64)
+        return _lib.problems_from_batch(self.profiles, rows, xm, ym, 0.0)
+
+    def is_f32(self):
+        """Per task: float32 fields in the reference (precision="single", no phase shift)?"""
+        sol = self.config.solver
+        if sol.precision == "double" or sol.footprint:
+            return np.zeros(len(self.tasks), dtype=bool)
+        return np.array([not (t.x * t.x + t.y * t.y > 0.0) for t, _ in self.tasks], dtype=bool)
+
+    def chunks(self, idx, per_task_bytes):
+        """Split the task indices ``idx`` into launches of at most MAX_CHUNK_BYTES / 256 problems."""
+        chunk = max(1, min(256, MAX_CHUNK_BYTES // max(per_task_bytes, 1)))
+        return [idx[c0:c0 + chunk] for c0 in range(0, len(idx), chunk)]
+
+    def row(self, t):
+        return self.profiles.row(self.task_group[t])
+
+
+def solve_tasks(config, tasks: Sequence[Tuple[object, int]], surface_flux=None, cache=None, out=None,
+                out_pinned=False) -> List[dict]:
+    """Solve the given (tower | tower index, met index) tasks on this process's GPU, batched.
+
+    ``out=(conc, flx)``: float64 destination arrays ``[len(tasks), nlv, ny, nx]`` (e.g. this rank's block of
+    a shared-memory segment) that receive the fields in task order; the result dicts then hold views.
+    """
+    dom, sol = config.domain, config.solver
+    tb = TaskBatch(config, tasks)
+    srf = _surface_flux(config, surface_flux)
+    results: List[dict] = [None] * len(tb.tasks)
+    domain = tb.domain
+
     pending = []
-    for t, (ti, mi) in enumerate(tasks):
-        tower = config.towers[ti]
-        met_step = config.met.get_step(mi)
-        key = (float(tower.z_m), int(mi))
-        if key not in prof_cache:
-            prof_cache[key] = _profiles_for(config, tower.z_m, met_step)
-        z, profiles = prof_cache[key]
+    for t, (tower, mi) in enumerate(tb.tasks):
         if cache is not None and sol.footprint:                       # solver.py:77-80
+            z, profiles = tb.row(t)
             hit = cache.get(z, profiles, domain, dom.modes, (tower.x, tower.y), dom.halo, sol.precision)
             if hit is not None:
-                results[t] = _result(tower, met_step, *hit)
+                results[t] = _result(tower, tb.steps[mi], *hit)
                 continue
-        pending.append((t, tower, met_step, z, profiles))
+        pending.append(t)
 
-    nlv = len(lv)
-    per_problem = 2 * nlv * dom.ny * dom.nx * 8
-    chunk = max(1, min(256, MAX_CHUNK_BYTES // max(per_problem, 1)))
+    nlv = tb.nlv
+    per_task = 2 * nlv * dom.ny * dom.nx * 8
+    is32 = tb.is_f32()
     # enqueue every chunk without waiting: the device->host copy of chunk k overlaps the kernels of
-    # chunk k+1 and the host-side profile work of the chunks after it
+    # chunk k+1 and the host-side work of the chunks after it.  Tasks the reference answers in float32
+    # (precision="single", tower at exactly (0,0)) and float64 ones go out as separate launches.
     inflight = []
-    for c0 in range(0, len(pending), chunk):
-        part = pending[c0:c0 + chunk]
-        conc, flx = solve_batched(
-            srf, [p[3] for p in part], [p[4] for p in part], domain, levels, modes=dom.modes,
-            meas_pts=[(p[1].x, p[1].y) for p in part], footprint=sol.footprint, analytic=sol.analytic,
-            halo=dom.halo, precision=sol.precision, wait=False)
-        inflight.append((part, conc, flx))
+    for want32 in (False, True):
+        idx = [t for t in pending if bool(is32[t]) == want32]
+        for part in tb.chunks(idx, per_task):
+            dest = None
+            if out is not None and not want32 and part == list(range(part[0], part[0] + len(part))):
+                dest = (out[0][part[0]:part[0] + len(part)], out[1][part[0]:part[0] + len(part)])
+            conc, flx = solve_batched(srf, problems=tb.problems(part), wait=False, out=dest,
+                                      out_pinned=out_pinned, **tb.solver_kw)
+            inflight.append((part, conc, flx, dest is not None))
     synchronize()
-    for part, conc, flx in inflight:
-        for b, (t, tower, met_step, z, profiles) in enumerate(part):
-            grid = make_grid(z, lv, domain, dom.nx, dom.ny)
+    for part, conc, flx, direct in inflight:
+        for b, t in enumerate(part):
+            tower, mi = tb.tasks[t]
+            z, profiles = tb.row(t)
+            if out is not None and not direct:
+                out[0][t] = conc[b]
+                out[1][t] = flx[b]
+            grid = make_grid(z, tb.lv, domain, dom.nx, dom.ny)
             res = (grid, np.squeeze(conc[b]), np.squeeze(flx[b]))
             if cache is not None and sol.footprint:                   # solver.py:301-302
                 cache.put(z, profiles, domain, dom.modes, (tower.x, tower.y), dom.halo, sol.precision, *res)
-            results[t] = _result(tower, met_step, *res)
+            results[t] = _result(tower, tb.steps[mi], *res)
     return results
 
 
 def run_bldfm_timeseries(config, tower, surface_flux=None) -> list:
-    """All timesteps for one tower (interface.py:141-174), one batched launch per chunk."""
+    """All timesteps for one tower (interface.py:141-174), one batched launch per chunk.  ``tower`` may be any
+    tower object (it need not be an entry of ``config.towers``, like in the reference)."""
     n = config.met.n_timesteps
     logger.info("Running timeseries for tower '%s': %d timesteps", tower.name, n)
-    ti = next(i for i, t in enumerate(config.towers) if t is tower or t == tower)
-    return solve_tasks(config, [(ti, i) for i in range(n)], surface_flux, _make_cache(config))
+    return solve_tasks(config, [(tower, i) for i in range(n)], surface_flux, _make_cache(config))
+
+
+def _multitower_tasks(config):
+    # timestep-major task order keeps the towers of one met step in the same batch
+    n = config.met.n_timesteps
+    return [(ti, mi) for mi in range(n) for ti in range(len(config.towers))]
 
 
 def run_bldfm_multitower(config, surface_flux=None) -> dict:
     """All towers x all timesteps (interface.py:177-207); marches shared between towers."""
     n = config.met.n_timesteps
     logger.info("Running multitower: %d towers x %d timesteps", len(config.towers), n)
-    # timestep-major task order keeps the towers of one met step in the same batch
-    tasks = [(ti, mi) for mi in range(n) for ti in range(len(config.towers))]
+    tasks = _multitower_tasks(config)
     flat = solve_tasks(config, tasks, surface_flux, _make_cache(config))
     out = {t.name: [None] * n for t in config.towers}
     for (ti, mi), res in zip(tasks, flat):
@@ -178,14 +269,28 @@ def run_bldfm_multitower(config, surface_flux=None) -> dict:
     return out
 
 
+def _shard(config, tasks):
+    """(rank, world, owner[t], my task indices): march groups spread over the ranks (distributed.shard_groups)."""
+    rank, ws = _dist.world()
+    keys, task_group = plan_tasks(config, tasks)
+    ntow = np.bincount(task_group, minlength=len(keys))
+    assign = _dist.shard_groups(keys, 1.0 + 0.15 * ntow, ws)     # march dominates, towers add a little
+    owner = _dist.owner_of_tasks(task_group, assign)
+    mine = [t for t in range(len(tasks)) if owner[t] == rank]
+    return rank, ws, owner, mine
+
+
 def run_bldfm_parallel(config, max_workers=None, parallel_over: str = "towers", surface_flux=None,
                        gather: bool = True) -> dict:
     """Multi-GPU counterpart of the reference's process pool (interface.py:241-326).
 
     Under ``torchrun`` (``torch.distributed`` initialised) the march groups are distributed over the
-    ranks (``distributed.shard_groups``), every rank solves its share on its own GPU, and the cropped
-    fields are gathered on rank 0 (other ranks return their local share only when ``gather=False``,
-    else an empty dict).  Without a process group this is ``run_bldfm_multitower`` on one GPU.
+    ranks (``distributed.shard_groups``), every rank solves its share on its own GPU and copies its fields
+    device->host over ITS OWN PCIe link straight into a page-locked shared-memory segment that rank 0 maps
+    (``distributed.SharedResults``): the final gather is that segment plus one barrier -- no field crosses a
+    PCIe link twice and none goes through another GPU.  Rank 0 returns the full result dict (arrays are views
+    into the segment), the other ranks an empty dict; ``gather=False`` returns each rank's own share.
+    Without a process group this is ``run_bldfm_multitower`` on one GPU.
     ``max_workers`` and ``parallel_over`` are accepted for compatibility; the strategies differ only
     in how the reference slices its task list, the results are identical (tests/test_parallel.py:78-90).
     """
@@ -201,54 +306,140 @@ def run_bldfm_parallel(config, max_workers=None, parallel_over: str = "towers", 
 
     n = config.met.n_timesteps
     towers = config.towers
-    tasks = [(ti, mi) for mi in range(n) for ti in range(len(towers))]
-    keys, task_group = plan_tasks(config, tasks)
-    ntow = np.bincount(task_group, minlength=len(keys))
-    assign = _dist.shard_groups(keys, 1.0 + 0.15 * ntow, ws)     # march dominates, towers add a little
-    owner = _dist.owner_of_tasks(task_group, assign)
-    mine = [t for t in range(len(tasks)) if owner[t] == rank]
-    local = solve_tasks(config, [tasks[t] for t in mine], None, None)
-
+    tasks = _multitower_tasks(config)
+    rank, ws, owner, mine = _shard(config, tasks)
     out = {t.name: [None] * n for t in towers}
     if not gather:
+        local = solve_tasks(config, [tasks[t] for t in mine], None, None)
         for t, res in zip(mine, local):
             ti, mi = tasks[t]
             out[towers[ti].name][mi] = res
         return out
 
-    def stack(key):
-        if not local:
-            return None
-        return np.stack([np.asarray(r[key]) for r in local])
-
-    probe = solve_shape(config)
-    conc_l = stack("conc") if local else np.empty((0,) + probe[0], probe[1])
-    flx_l = stack("flx") if local else np.empty((0,) + probe[0], probe[1])
-    conc_all = _dist.gather_fields(conc_l, owner)
-    flx_all = _dist.gather_fields(flx_l, owner)
+    shape, _ = solve_shape(config)
+    lv = _levels(config)
+    nlv = 1 if np.ndim(lv) == 0 else len(lv)
+    dom = config.domain
+    counts = np.bincount(owner, minlength=ws)
+    seg = _dist.SharedResults.acquire((nlv, dom.ny, dom.nx), counts)
+    conc_l, flx_l = seg.local_block()
+    local = solve_tasks(config, [tasks[t] for t in mine], None, None, out=(conc_l, flx_l),
+                        out_pinned=seg.pinned)
+    seg.barrier()                                  # every rank's fields have landed in the segment
     if rank != 0:
         return {}
-    lv = _levels(config)
-    lv = np.array([lv]) if np.ndim(lv) == 0 else np.asarray(lv)
-    dom = config.domain
-    for t, (ti, mi) in enumerate(tasks):
-        tower = towers[ti]
-        met_step = config.met.get_step(mi)
-        z, _ = _profiles_for(config, tower.z_m, met_step)
-        grid = make_grid(z, lv, (dom.xmax, dom.ymax), dom.nx, dom.ny)
-        out[tower.name][mi] = _result(tower, met_step, grid, conc_all[t], flx_all[t])
+    conc_all, flx_all = seg.all_blocks()           # rank-major: rank r's tasks in its own task order
+    start = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    pos = np.empty(len(tasks), dtype=np.int64)     # task -> row of the rank-major segment
+    fill = start.copy()
+    for t in range(len(tasks)):
+        pos[t] = fill[owner[t]]
+        fill[owner[t]] += 1
+    tb = TaskBatch(config, tasks)
+    is32 = tb.is_f32()
+    lvarr = tb.lv
+    for t, (tower, mi) in enumerate(tb.tasks):
+        z, _ = tb.row(t)
+        grid = make_grid(z, lvarr, (dom.xmax, dom.ymax), dom.nx, dom.ny)
+        c, f = np.squeeze(conc_all[pos[t]]), np.squeeze(flx_all[pos[t]])
+        if is32[t]:
+            c, f = c.astype(np.float32), f.astype(np.float32)
+        out[tower.name][mi] = _result(tower, tb.steps[mi], grid, c, f)
     return out
 
 
 def solve_shape(config):
-    """(shape, dtype) of one task's squeezed conc/flx field."""
-    from . import _lib
-
+    """(shape, dtype) of one task's squeezed conc/flx field (dtype of a shifted tower)."""
     dom, sol = config.domain, config.solver
     lv = _levels(config)
     nlv = 1 if np.ndim(lv) == 0 else len(lv)
     shape = tuple(s for s in (nlv, dom.ny, dom.nx) if s != 1)
-    flags = (_lib.FOOTPRINT if sol.footprint else 0) | (_lib.DOUBLE if sol.precision == "double" else 0)
-    t0 = config.towers[0]
-    f32 = bool(_lib.lib().bldfm_output_is_f32(flags, float(t0.x), float(t0.y)))
-    return shape, (np.float32 if f32 else np.float64)
+    return shape, np.float64
+
+
+# ------------------------------------------------------------------------------------------------
+# reductions on the device (SURVEY.md f-4)
+# ------------------------------------------------------------------------------------------------
+
+def run_bldfm_measure(config, flux_map, chunk_groups: int = 8) -> dict:
+    """Tower measurements without moving footprints: for every tower and timestep
+    ``sum(conc * flux_map)`` and ``sum(flx * flux_map)`` -- ``point_measurement`` (utils.py:80-92) fused on
+    the device.  Returns ``{tower_name: {"conc": [n_time(, nlv)], "flx": [...]}}`` on rank 0 (every rank
+    when not distributed); under torchrun the march groups are sharded and only these scalars are gathered.
+    """
+    towers = config.towers
+    n = config.met.n_timesteps
+    tasks = _multitower_tasks(config)
+    rank, ws, owner, mine = _shard(config, tasks)
+    tb = TaskBatch(config, [tasks[t] for t in mine])
+    srf = _surface_flux(config, None)
+    is32 = tb.is_f32()
+    ntow = max(1, len(towers))
+    parts = []
+    for want32 in (False, True):
+        idx = [t for t in range(len(tb.tasks)) if bool(is32[t]) == want32]
+        step = max(1, chunk_groups * ntow)
+        for c0 in range(0, len(idx), step):
+            part = idx[c0:c0 + step]
+            cw, fw = measure_batched(flux_map, srf, problems=tb.problems(part), wait=False, **tb.solver_kw)
+            parts.append((part, cw, fw))
+    synchronize()
+    nlv = tb.nlv
+    loc = np.zeros((len(mine), 2, nlv))
+    for part, cw, fw in parts:
+        loc[part, 0] = cw
+        loc[part, 1] = fw
+    full = _dist.gather_small(loc, owner)
+    if full is None:
+        return {}
+    out = {t.name: {"conc": np.empty((n, nlv)), "flx": np.empty((n, nlv))} for t in towers}
+    for t, (ti, mi) in enumerate(tasks):
+        out[towers[ti].name]["conc"][mi] = full[t, 0]
+        out[towers[ti].name]["flx"][mi] = full[t, 1]
+    if nlv == 1:
+        for v in out.values():
+            v["conc"], v["flx"] = v["conc"][:, 0], v["flx"][:, 0]
+    return out
+
+
+def run_bldfm_aggregate(config, chunk_groups: int = 8) -> dict:
+    """Footprint climatology: the time-mean ``conc`` / ``flx`` field of every tower
+    (examples/timeseries_example.py:46: ``np.mean([r["flx"] for r in results], axis=0)``), summed on the device
+    -- one field per tower crosses PCIe instead of one per timestep.  Under torchrun every rank sums its own
+    timesteps and the per-tower sums are reduced onto rank 0 over NCCL (the one collective of this driver).
+    Returns ``{tower_name: {"grid": (X, Y), "conc": mean, "flx": mean, "n": n_time}}`` on rank 0.
+    """
+    towers = config.towers
+    dom, sol = config.domain, config.solver
+    n = config.met.n_timesteps
+    tasks = _multitower_tasks(config)
+    rank, ws, owner, mine = _shard(config, tasks)
+    tb = TaskBatch(config, [tasks[t] for t in mine])
+    srf = _surface_flux(config, None)
+    acc = FieldAccumulator((dom.ny, dom.nx), tb.domain, tb.levels, len(towers), modes=dom.modes,
+                           footprint=sol.footprint, analytic=sol.analytic, halo=dom.halo, precision=sol.precision)
+    try:
+        is32 = tb.is_f32()
+        slot = np.array([tasks[t][0] for t in mine], dtype=np.int32)
+        step = max(1, chunk_groups * max(1, len(towers)))
+        for want32 in (False, True):
+            idx = [t for t in range(len(tb.tasks)) if bool(is32[t]) == want32]
+            for c0 in range(0, len(idx), step):
+                part = idx[c0:c0 + step]
+                acc.add(srf, slot[part], problems=tb.problems(part))
+        if ws > 1:
+            sums = _dist.reduce_device_sums(acc)
+        else:
+            sums = acc.fetch()
+    finally:
+        acc.close()
+    if sums is None:
+        return {}
+    x = np.linspace(0, dom.xmax, dom.nx, endpoint=False)
+    y = np.linspace(0, dom.ymax, dom.ny, endpoint=False)
+    Y, X = np.meshgrid(y, x, indexing="ij")
+    out = {}
+    for ti, tower in enumerate(towers):
+        out[tower.name] = {"grid": (X, Y), "conc": np.squeeze(sums[0][ti] / n), "flx": np.squeeze(sums[1][ti] / n),
+                           "n": n}
+    return out

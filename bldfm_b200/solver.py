@@ -33,8 +33,10 @@ def _flags(footprint, analytic, precision):
         f |= _lib.ANALYTIC
     if config.MARCH_MODE == "fma":
         f |= _lib.MARCH_FMA
+    elif config.MARCH_MODE == "auto":
+        f |= _lib.MARCH_AUTO
     elif config.MARCH_MODE != "exact":
-        raise ValueError("bldfm_b200.config.MARCH_MODE must be 'exact' or 'fma'")
+        raise ValueError("bldfm_b200.config.MARCH_MODE must be 'exact', 'fma' or 'auto'")
     if config.FFT_LIBRARY:
         f |= _lib.FFT_LIBRARY
     if config.FFT_FULL:
@@ -192,9 +194,36 @@ def steady_state_transport_solver(
     return result
 
 
-def solve_batched(srf_flx, zs, profiles_list, domain, levels, modes=(512, 512), meas_pts=None,
+def _problem_array(zs, profiles_list, meas_pts, bg):
+    """ctypes array of ``bldfm_problem`` built problem by problem (general, per-problem Python cost)."""
+    probs, keep = [], []
+    for b in range(len(zs)):
+        p, k = _lib.make_problem(zs[b], profiles_list[b], meas_pts[b], bg[b])
+        probs.append(p)
+        keep.append(k)
+    parr = (_lib.Problem * len(probs))(*probs)
+    return parr, keep
+
+
+def _problem_view(problems):
+    """(address, count, numpy view with the fields of bldfm_problem) of a problem array given either as the
+    structured array of ``_lib.problems_from_batch`` or as a ctypes ``Problem`` array."""
+    if isinstance(problems, np.ndarray):
+        return problems.ctypes.data, len(problems), problems
+    view = np.frombuffer(problems, dtype=_lib.PROBLEM_DTYPE)
+    return C.addressof(problems), len(problems), view
+
+
+def _is_f32(flags, view):
+    """Per problem: would the reference return float32 fields (solver.py:177-185,254-262)?"""
+    if flags & (_lib.DOUBLE | _lib.FOOTPRINT):
+        return np.zeros(len(view), dtype=bool)
+    return ~(view["xm"] * view["xm"] + view["ym"] * view["ym"] > 0.0)
+
+
+def solve_batched(srf_flx, zs=None, profiles_list=None, domain=None, levels=None, modes=(512, 512), meas_pts=None,
                   srf_bg_conc=0.0, footprint=False, analytic=False, halo=None, precision="single",
-                  wait=True):
+                  wait=True, problems=None, out=None, out_pinned=False):
     """Many (tower, met) conditions in ONE launch (C entry point ``bldfm_solve_batched``).
 
     ``zs[b]``, ``profiles_list[b]``, ``meas_pts[b]`` describe problem b; everything else is shared.
@@ -202,17 +231,17 @@ def solve_batched(srf_flx, zs, profiles_list, domain, levels, modes=(512, 512), 
     ``(conc, flx)`` of shape ``[B, nlv, ny, nx]`` (float32 only for precision="single" without any
     phase shift, like the single-problem solver).
 
+    ``problems=(array, keepalive)`` from ``_lib.problems_from_batch`` replaces ``zs/profiles_list/meas_pts``
+    (no per-problem Python work).  ``out=(conc, flx)`` are caller-provided destination arrays
+    ``[B, nlv, ny, nx]`` of the result dtype (e.g. slices of a shared-memory segment); ``out_pinned=True``
+    states that they are page-locked, which ``wait=False`` needs.
+
     ``wait=False`` only enqueues the work: the returned arrays (pinned host memory) are valid after
     ``synchronize()``; the device->host copy of this batch then overlaps the kernels of the next one.
     Keep the returned arrays referenced until then -- a dropped array hands its buffer back to the pool.
     """
     q0 = np.asarray(srf_flx)
     ny, nx = q0.shape
-    B = len(zs)
-    if B < 1:
-        raise ValueError("solve_batched needs at least one problem")
-    if meas_pts is None:
-        meas_pts = [(0.0, 0.0)] * B
     geom = _geometry(q0.shape, domain, modes, halo)
     if geom.clamped:
         logger.info("Warning: Number of Fourier modes must not exeed number of grid cells.")
@@ -220,24 +249,55 @@ def solve_batched(srf_flx, zs, profiles_list, domain, levels, modes=(512, 512), 
     flags = _flags(footprint, analytic, precision)
     _, lv64 = _levels_array(levels)
     nlv = len(lv64)
-    bg = srf_bg_conc if np.ndim(srf_bg_conc) else [srf_bg_conc] * B
-    probs, keep = [], []
-    for b in range(B):
-        p, k = _lib.make_problem(zs[b], profiles_list[b], meas_pts[b], bg[b])
-        probs.append(p)
-        keep.append(k)
-    f32 = all(bool(_lib.lib().bldfm_output_is_f32(flags, p.xm, p.ym)) for p in probs)
+    if problems is None:
+        B = len(zs)
+        if B < 1:
+            raise ValueError("solve_batched needs at least one problem")
+        if meas_pts is None:
+            meas_pts = [(0.0, 0.0)] * B
+        bg = srf_bg_conc if np.ndim(srf_bg_conc) else [srf_bg_conc] * B
+        parr, keep = _problem_array(zs, profiles_list, meas_pts, bg)
+    else:
+        parr, keep = problems
+    addr, B, view = _problem_view(parr)
+    if B < 1:
+        raise ValueError("solve_batched needs at least one problem")
+    is32 = _is_f32(flags, view)
+    f32 = bool(is32.all())
+    if is32.any() and not f32:
+        # precision="single" with some towers at exactly (0,0) and some shifted: the reference returns
+        # float32 fields for the former and float64 for the latter (solver.py:177-185,254-262).  One launch
+        # holds one dtype, so the two kinds go out as two sub-batches; the merged array is float64 (the
+        # float32 values are represented exactly) and the drivers hand each task its reference dtype back.
+        if out is None:
+            out = (np.empty((B, nlv, ny, nx), np.float64), np.empty((B, nlv, ny, nx), np.float64))
+        for want in (True, False):
+            idx = np.nonzero(is32 == want)[0]
+            sub = np.ascontiguousarray(view[idx])
+            c, f = solve_batched(srf_flx, domain=domain, levels=levels, modes=modes, footprint=footprint,
+                                 analytic=analytic, halo=halo, precision=precision, wait=True,
+                                 problems=(sub, keep))
+            out[0][idx] = c
+            out[1][idx] = f
+        return out
     dt = np.float32 if f32 else np.float64
-    conc = _pinned_pool.empty((B, nlv, ny, nx), dt)
-    flx = _pinned_pool.empty((B, nlv, ny, nx), dt)
+    if out is None:
+        conc, pinned_c = _pinned_pool.empty2((B, nlv, ny, nx), dt)
+        flx, pinned_f = _pinned_pool.empty2((B, nlv, ny, nx), dt)
+        pinned = pinned_c and pinned_f
+    else:
+        conc, flx = out
+        for a in (conc, flx):
+            if a.shape != (B, nlv, ny, nx) or a.dtype != dt or not a.flags.c_contiguous:
+                raise ValueError(f"out arrays must be C-contiguous {dt.__name__} of shape {(B, nlv, ny, nx)}")
+        pinned = bool(out_pinned)
     src = None if footprint else _lib.as_f64(q0)
-    parr = (_lib.Problem * B)(*probs)
     plan = get_fft_manager().plan(geom)
-    if not wait:
-        flags |= _lib.ASYNC
+    if not wait and pinned:
+        flags |= _lib.ASYNC           # pageable destinations are copied synchronously (see BLDFM_ASYNC)
     _lib.check(_lib.lib().bldfm_solve_batched(
-        plan, B, parr, lv64.ctypes.data_as(C.POINTER(C.c_int64)), nlv,
-        None if src is None else _lib.ptr(src), flags, _lib.ptr(conc), _lib.ptr(flx)))
+        plan, B, addr, _levels_ptr(lv64), nlv,
+        None if src is None else _lib.ptr(src), flags, conc.ctypes.data, flx.ctypes.data))
     del keep
     return conc, flx
 
@@ -249,8 +309,9 @@ def synchronize():
         _lib.check(_lib.lib().bldfm_plan_synchronize(h))
 
 
-def measure_batched(weight, srf_flx, zs, profiles_list, domain, levels, modes=(512, 512), meas_pts=None,
-                    srf_bg_conc=0.0, footprint=False, analytic=False, halo=None, precision="single", wait=True):
+def measure_batched(weight, srf_flx, zs=None, profiles_list=None, domain=None, levels=None, modes=(512, 512),
+                    meas_pts=None, srf_bg_conc=0.0, footprint=False, analytic=False, halo=None, precision="single",
+                    wait=True, problems=None):
     """``point_measurement`` (utils.py:80-92) fused on the device for a batch of solves.
 
     Returns ``(conc_w, flx_w)`` of shape ``[B, nlv]``: ``sum(conc[b, l] * weight)`` and
@@ -261,9 +322,6 @@ def measure_batched(weight, srf_flx, zs, profiles_list, domain, levels, modes=(5
     and the host can prepare the next batch while this one runs.
     """
     q0 = np.asarray(srf_flx)
-    B = len(zs)
-    if meas_pts is None:
-        meas_pts = [(0.0, 0.0)] * B
     w = _lib.as_f64(weight)
     if w.shape != q0.shape:
         raise ValueError("weight must have the shape of srf_flx")
@@ -271,12 +329,19 @@ def measure_batched(weight, srf_flx, zs, profiles_list, domain, levels, modes=(5
     flags = _flags(footprint, analytic, precision)
     _, lv64 = _levels_array(levels)
     nlv = len(lv64)
-    bg = srf_bg_conc if np.ndim(srf_bg_conc) else [srf_bg_conc] * B
-    probs, keep = [], []
-    for b in range(B):
-        p, k = _lib.make_problem(zs[b], profiles_list[b], meas_pts[b], bg[b])
-        probs.append(p)
-        keep.append(k)
+    if problems is None:
+        B = len(zs)
+        if meas_pts is None:
+            meas_pts = [(0.0, 0.0)] * B
+        bg = srf_bg_conc if np.ndim(srf_bg_conc) else [srf_bg_conc] * B
+        parr, keep = _problem_array(zs, profiles_list, meas_pts, bg)
+    else:
+        parr, keep = problems
+    addr, B, view = _problem_view(parr)
+    is32 = _is_f32(flags, view)
+    if is32.any() and not is32.all():
+        raise ValueError("measure_batched: precision='single' batch mixes towers at (0,0) with shifted ones; "
+                         "pass them as separate batches")
     if wait:
         conc_w = np.empty((B, nlv))
         flx_w = np.empty((B, nlv))
@@ -285,13 +350,106 @@ def measure_batched(weight, srf_flx, zs, profiles_list, domain, levels, modes=(5
         flx_w = _pinned_pool.empty((B, nlv), np.float64)
         flags |= _lib.ASYNC
     src = None if footprint else _lib.as_f64(q0)
-    parr = (_lib.Problem * B)(*probs)
     plan = get_fft_manager().plan(geom)
     _lib.check(_lib.lib().bldfm_solve_batched_measure(
-        plan, B, parr, lv64.ctypes.data_as(C.POINTER(C.c_int64)), nlv,
+        plan, B, addr, _levels_ptr(lv64), nlv,
         None if src is None else _lib.ptr(src), flags, _lib.ptr(w), _lib.ptr(conc_w), _lib.ptr(flx_w)))
     del keep
     return conc_w, flx_w
+
+
+class FieldAccumulator:
+    """Device-resident sums of solved fields per slot -- time aggregation of footprints without moving the
+    individual fields to the host (examples/timeseries_example.py:46 does
+    ``np.mean([r["flx"] for r in results], axis=0)`` on the host).
+
+    ``add(...)`` solves a batch and adds problem b's ``conc``/``flx`` to slot ``slot_of[b]`` in problem order;
+    ``fetch()`` returns the sums ``[nslots, nlv, ny, nx]`` (float64); ``device_pointers()`` exposes them for a
+    cross-rank reduction.
+    """
+
+    def __init__(self, shape, domain, levels, nslots, modes=(512, 512), footprint=False, analytic=False,
+                 halo=None, precision="single"):
+        self.shape = tuple(shape)
+        self.domain, self.levels, self.modes, self.halo = domain, levels, modes, halo
+        self.footprint, self.analytic, self.precision = footprint, analytic, precision
+        self.geom = _geometry(self.shape, domain, modes, halo)
+        _, self.lv64 = _levels_array(levels)
+        self.nlv = len(self.lv64)
+        self.nslots = int(nslots)
+        self.device = config.DEVICE
+        self.count = np.zeros(self.nslots, dtype=np.int64)
+        ny, nx = self.shape
+        self.nbytes = self.nslots * self.nlv * ny * nx * 8
+        L = _lib.lib()
+        self._ptr = []
+        for _ in range(2):
+            p = C.c_void_p()
+            _lib.check(L.bldfm_device_alloc(self.device, self.nbytes, C.byref(p)))
+            self._ptr.append(p.value)
+        self.reset()
+
+    def reset(self):
+        for p in self._ptr:
+            _lib.check(_lib.lib().bldfm_device_memset(self.device, p, 0, self.nbytes))
+        self.count[:] = 0
+
+    def device_pointers(self):
+        return tuple(self._ptr)
+
+    def add(self, srf_flx, slot_of, problems=None, zs=None, profiles_list=None, meas_pts=None, srf_bg_conc=0.0):
+        flags = _flags(self.footprint, self.analytic, self.precision) | _lib.ASYNC
+        if problems is None:
+            B = len(zs)
+            if meas_pts is None:
+                meas_pts = [(0.0, 0.0)] * B
+            bg = srf_bg_conc if np.ndim(srf_bg_conc) else [srf_bg_conc] * B
+            parr, keep = _problem_array(zs, profiles_list, meas_pts, bg)
+        else:
+            parr, keep = problems
+        addr, B, view = _problem_view(parr)
+        is32 = _is_f32(flags, view)
+        if is32.any() and not is32.all():
+            raise ValueError("FieldAccumulator.add: batch mixes float32 and float64 tasks; add them separately")
+        slots = np.ascontiguousarray(slot_of, dtype=np.int32)
+        if slots.shape != (B,):
+            raise ValueError("slot_of must have one entry per problem")
+        src = None if self.footprint else _lib.as_f64(np.asarray(srf_flx))
+        plan = get_fft_manager().plan(self.geom)
+        self._plan = plan
+        _lib.check(_lib.lib().bldfm_solve_batched_accumulate(
+            plan, B, addr, _levels_ptr(self.lv64), self.nlv, None if src is None else _lib.ptr(src), flags,
+            _lib.ptr(slots), self.nslots, self._ptr[0], self._ptr[1]))
+        np.add.at(self.count, slots[slots >= 0], 1)
+        del keep
+
+    def synchronize(self):
+        plan = getattr(self, "_plan", None)
+        if plan is not None:
+            _lib.check(_lib.lib().bldfm_plan_synchronize(plan))
+
+    def fetch(self):
+        """(conc_sum, flx_sum) ``[nslots, nlv, ny, nx]`` float64 on the host (synchronises)."""
+        L = _lib.lib()
+        self.synchronize()
+        ny, nx = self.shape
+        out = []
+        for p in self._ptr:
+            a = np.empty((self.nslots, self.nlv, ny, nx), np.float64)
+            _lib.check(L.bldfm_memcpy_d2h(self.device, _lib.ptr(a), p, self.nbytes))
+            out.append(a)
+        return tuple(out)
+
+    def close(self):
+        for p in self._ptr:
+            _lib.lib().bldfm_device_free(self.device, C.c_void_p(p))
+        self._ptr = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def spectral_fields(srf_flx, z, profiles, domain, levels, modes=(512, 512), meas_pt=(0.0, 0.0),

@@ -48,6 +48,10 @@ extern "C" {
                                          solve's kernels (double-buffered device results, separate copy stream) */
 #define BLDFM_FFT_LIBRARY      0x080  /* force the cuFFT transform path instead of the pruned in-house kernels    */
 #define BLDFM_FFT_FULL         0x100  /* in-house back-transform without the real-output (Hermitian) halving      */
+#define BLDFM_MARCH_AUTO       0x400  /* FMA-contracted march where linear shooting is well conditioned (kappa at the
+                                         highest output level <= bldfm_auto_kappa_limit() for every march of the
+                                         call: predicted deviation from the reference <= 1e-11 rel-L2, SURVEY.md
+                                         Appendix C), the bit-mirrored march otherwise                          */
 #define BLDFM_MARCH_FULL       0x200  /* march every retained mode instead of the half-plane ky <= nly/2 whose
                                          conjugates fill the other half (cross-check; same values bit for bit)  */
 
@@ -149,6 +153,23 @@ int  bldfm_solve_batched_measure(bldfm_plan *plan, int32_t nprob, const bldfm_pr
                                  const int64_t *levels, int32_t nlv, const double *srf_flx, int flags,
                                  const double *weight, double *conc_w, double *flx_w);
 
+/* Time aggregation without moving the fields to the host (examples/timeseries_example.py:46,
+ * np.mean([r["flx"] for r in results], axis=0)): solves the batch and adds every problem's fields to
+ * accumulator slot slot_of[b] (problem order; slot_of[b] < 0 skips the problem).
+ *   slot_of       host [nprob] int32
+ *   acc_conc/flx  DEVICE [nslots][nlv][ny][nx] float64, caller-owned (bldfm_device_alloc / bldfm_device_memset);
+ *                 ordered on the plan's stream, BLDFM_ASYNC skips the final synchronisation. */
+int  bldfm_solve_batched_accumulate(bldfm_plan *plan, int32_t nprob, const bldfm_problem *probs,
+                                    const int64_t *levels, int32_t nlv, const double *srf_flx, int flags,
+                                    const int32_t *slot_of, int32_t nslots, double *acc_conc, double *acc_flx);
+
+/* Conditioning number kappa(z[level]) of linear shooting for one problem (pure host arithmetic, usable without
+ * a GPU): what BLDFM_MARCH_AUTO compares with bldfm_auto_kappa_limit() (default 8.5, env BLDFM_B200_AUTO_KAPPA).
+ * bldfm_plan_last_march_mode: 1 if the plan's most recent march ran FMA-contracted, 0 if bit-mirrored. */
+int    bldfm_kappa(const bldfm_geometry *g, const bldfm_problem *prob, int32_t level, double *kappa);
+double bldfm_auto_kappa_limit(void);
+int    bldfm_plan_last_march_mode(const bldfm_plan *plan);
+
 /* One OVERSIZED problem sharded by ky-slab over `nranks` GPUs (one process per GPU); replaces nothing
  * in the reference -- it scales a single steady_state_transport_solver call (src/bldfm/solver.py:16)
  * beyond one device.  float64.  In non-footprint mode every rank holds the whole source srf_flx and computes only
@@ -171,6 +192,15 @@ int  bldfm_sharded_stage1(bldfm_plan *plan, const bldfm_problem *prob, const int
                           void *const *peer_p, void *const *peer_q);
 int  bldfm_sharded_stage2(bldfm_plan *plan, int32_t nlv, int flags, int32_t rank, int32_t nranks,
                           const void *recv_p, const void *recv_q, void *conc_slab, void *flx_slab);
+/* Device-side synchronisation of the fused transpose, enqueued on the plan's stream (no host thread, no
+ * collective): after stage 1, bldfm_peer_signal stores `value` (the solve's sequence number) into
+ * *peer_slots[d] for every rank d -- peer_slots is a DEVICE array of nranks pointers to this rank's slot in
+ * each peer's flag array (uint64, IPC-mapped); before stage 2, bldfm_peer_wait spins until all nranks slots
+ * of this rank's own flag array are >= value.  A peer that never arrives within timeout_s (<= 0: 20 s) ends
+ * the wait and is reported by bldfm_peer_status (1 + slot index, 0 = fine; synchronises the stream). */
+int  bldfm_peer_signal(bldfm_plan *plan, void *const *peer_slots, int32_t nranks, uint64_t value);
+int  bldfm_peer_wait(bldfm_plan *plan, const void *flags, int32_t nranks, uint64_t value, double timeout_s);
+int  bldfm_peer_status(bldfm_plan *plan, int32_t *status);
 /* CUDA IPC helpers for the fused transpose (device memory from bldfm_device_alloc only). */
 int  bldfm_ipc_export(void *dev_ptr, unsigned char *handle64);
 int  bldfm_ipc_open(int device, const unsigned char *handle64, void **out);
@@ -202,6 +232,10 @@ int  bldfm_host_alloc(int64_t bytes, void **out);      /* pinned host memory */
 int  bldfm_host_free(void *p);
 int  bldfm_device_alloc(int device, int64_t bytes, void **out);
 int  bldfm_device_free(int device, void *p);
+int  bldfm_device_memset(int device, void *p, int value, int64_t bytes);
+/* page-lock caller memory (e.g. a shared-memory segment the ranks of a node deliver their results into) */
+int  bldfm_host_register(void *p, int64_t bytes);
+int  bldfm_host_unregister(void *p);
 int  bldfm_memcpy_d2h(int device, void *dst_host, const void *src_dev, int64_t bytes);
 int  bldfm_memcpy_h2d(int device, void *dst_dev, const void *src_host, int64_t bytes);
 

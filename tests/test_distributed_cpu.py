@@ -39,16 +39,21 @@ def _fake_config():
                   SolverOptions(footprint=True, precision="double"), Parallel())
 
 
-def _fake_solve_tasks(config, tasks, surface_flux=None, cache=None):
-    """Stand-in for the CUDA path: fields are a deterministic function of (tower, met index)."""
+def _fake_solve_tasks(config, tasks, surface_flux=None, cache=None, out=None, out_pinned=False):
+    """Stand-in for the CUDA path: fields are a deterministic function of (tower, met index); like the real
+    ``solve_tasks`` it delivers them into ``out`` (this rank's block of the shared-memory segment)."""
     from bldfm_b200 import interface
-    out = []
-    for ti, mi in tasks:
+    res = []
+    for k, (ti, mi) in enumerate(tasks):
         tower = config.towers[ti]
         step = config.met.get_step(mi)
         base = np.arange(12 * 16, dtype=np.float64).reshape(12, 16)
-        out.append(interface._result(tower, step, (None, None, None), base * (ti + 1) + mi, base - 7 * ti + mi * mi))
-    return out
+        conc, flx = base * (ti + 1) + mi, base - 7 * ti + mi * mi
+        if out is not None:
+            out[0][k, 0] = conc
+            out[1][k, 0] = flx
+        res.append(interface._result(tower, step, (None, None, None), conc, flx))
+    return res
 
 
 def _worker(rank, world, port, q):
@@ -59,11 +64,20 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         interface.solve_tasks = _fake_solve_tasks
-        interface.solve_shape = lambda cfg: ((12, 16), np.float64)
         interface.make_grid = lambda *a, **k: (None, None, None)
-        interface._profiles_for = lambda cfg, zm, step: (np.zeros(3), None)
         cfg = _fake_config()
         res = interface.run_bldfm_parallel(cfg, parallel_over="both")
+        # a second call while the first result is alive must not overwrite it (fresh segment) ...
+        res2 = interface.run_bldfm_parallel(cfg, parallel_over="towers")
+        if rank == 0:
+            a, b = res["A"][1]["conc"], res2["A"][1]["conc"]
+            assert np.array_equal(a, b) and not np.shares_memory(a, b)
+        # ... and once both are dropped the cached segment is reused
+        del res2
+        res3 = interface.run_bldfm_parallel(cfg, parallel_over="towers")
+        if rank == 0:
+            assert np.array_equal(res3["B"][4]["flx"], res["B"][4]["flx"])
+        del res3
         part = interface.run_bldfm_parallel(cfg, parallel_over="time", gather=False)
         nloc = sum(r is not None for lst in part.values() for r in lst)
         if rank == 0:

@@ -111,3 +111,82 @@ def test_measure_batched_equals_point_measurement(gpu_lib):
     bldfm_b200.solver.synchronize()
     assert np.array_equal(cw2, cw) and np.array_equal(fw2, fw)
     assert np.allclose(fw3, 2.0 * fw, rtol=1e-13, atol=0.0)
+
+
+def test_single_precision_batch_mixes_origin_and_shifted_towers(gpu_lib):
+    """precision="single", footprint=False: a tower at exactly (0,0) gets float32 fields, shifted towers
+    float64 (solver.py:177-185,254-262); the batched drivers must accept the mix and keep each task's dtype."""
+    import bldfm_b200
+    from bldfm_b200.schema import Tower
+    cfg = _config(footprint=False, precision="single")
+    cfg.towers = [Tower("O", 10.0, 0.0, 0.0), cfg.towers[0], Tower("O2", 10.0, 0.0, 0.0), cfg.towers[1]]
+    res = bldfm_b200.run_bldfm_multitower(cfg)
+    for tower in cfg.towers:
+        want = np.float32 if (tower.x, tower.y) == (0.0, 0.0) else np.float64
+        for mi, r in enumerate(res[tower.name]):
+            single = bldfm_b200.run_bldfm_single(cfg, tower, met_index=mi)
+            assert r["conc"].dtype == want == single["conc"].dtype and r["flx"].dtype == want
+            assert np.array_equal(r["conc"], single["conc"]) and np.array_equal(r["flx"], single["flx"])
+    # the low-level entry point merges the two sub-batches into one float64 array
+    from bldfm_b200.pbl_model import vertical_profiles
+    z, prof = vertical_profiles(16, 10.0, (3.0, -2.0), ustar=0.4, mol=-60.0)
+    src = bldfm_b200.ideal_source((64, 48), (960.0, 720.0))
+    kw = dict(domain=(960.0, 720.0), levels=16, modes=(64, 48), footprint=False, precision="single")
+    conc, flx = bldfm_b200.solve_batched(src, [z] * 3, [prof] * 3, meas_pts=[(0.0, 0.0), (300.0, 200.0), (0.0, 0.0)], **kw)
+    assert conc.dtype == np.float64
+    _, c0, f0 = bldfm_b200.steady_state_transport_solver(src, z, prof, meas_pt=(0.0, 0.0), **kw)
+    _, c1, f1 = bldfm_b200.steady_state_transport_solver(src, z, prof, meas_pt=(300.0, 200.0), **kw)
+    assert c0.dtype == np.float32 and c1.dtype == np.float64
+    assert np.array_equal(conc[0, 0], c0) and np.array_equal(conc[2, 0], c0) and np.array_equal(flx[1, 0], f1)
+
+
+def test_timeseries_accepts_a_tower_outside_the_config(gpu_lib):
+    import bldfm_b200
+    from bldfm_b200.schema import Tower
+    cfg = _config()
+    other = Tower("X", 8.0, 333.0, 222.0)
+    res = bldfm_b200.run_bldfm_timeseries(cfg, other)
+    assert len(res) == 4 and res[0]["tower_name"] == "X"
+    single = bldfm_b200.run_bldfm_single(cfg, other, met_index=3)
+    assert np.array_equal(res[3]["flx"], single["flx"])
+
+
+def test_measure_sees_in_place_edits_of_the_weight_map(gpu_lib):
+    """The weight map is uploaded on every call: a localised in-place edit of the same buffer must show."""
+    import bldfm_b200
+    from bldfm_b200.pbl_model import vertical_profiles
+    from bldfm_b200.utils import ideal_source, point_measurement
+    dom = (960.0, 720.0)
+    w = ideal_source((64, 48), dom, shape="circle") + 0.1
+    z, p = vertical_profiles(16, 10.0, (3.0, -2.0), ustar=0.4, mol=-60.0)
+    kw = dict(domain=dom, levels=16, modes=(64, 48), footprint=True, precision="double")
+    _, flx = bldfm_b200.solve_batched(np.zeros((48, 64)), [z], [p], meas_pts=[(300.0, 350.0)], **kw)
+    _, f1 = bldfm_b200.measure_batched(w, np.zeros((48, 64)), [z], [p], meas_pts=[(300.0, 350.0)], **kw)
+    w[17, 23] += 5.0                      # one cell, same buffer, same address
+    _, f2 = bldfm_b200.measure_batched(w, np.zeros((48, 64)), [z], [p], meas_pts=[(300.0, 350.0)], **kw)
+    assert abs(f2[0, 0] - point_measurement(flx[0, 0], w)) <= 1e-12 * abs(f2[0, 0])
+    assert abs((f2[0, 0] - f1[0, 0]) - 5.0 * flx[0, 0, 17, 23]) <= 1e-9 * abs(5.0 * flx[0, 0, 17, 23])
+
+
+def test_measure_and_aggregate_drivers_match_host_reductions(gpu_lib, oracle):
+    """f-4: run_bldfm_measure == point_measurement of each footprint; run_bldfm_aggregate == np.mean over the
+    timesteps (examples/timeseries_example.py:46) of the delivered fields AND of the oracle's fields."""
+    import bldfm_b200
+    from bldfm_b200 import interface
+    from bldfm_b200.utils import ideal_source, point_measurement
+    cfg = _config(footprint=True)
+    flux_map = ideal_source((64, 48), (960.0, 720.0), shape="circle") + 0.05
+    full = bldfm_b200.run_bldfm_multitower(cfg)
+    meas = interface.run_bldfm_measure(cfg, flux_map, chunk_groups=2)
+    agg = interface.run_bldfm_aggregate(cfg, chunk_groups=2)
+    for tower in cfg.towers:
+        for mi in range(4):
+            want = point_measurement(full[tower.name][mi]["flx"], flux_map)
+            assert abs(meas[tower.name]["flx"][mi] - want) <= 1e-12 * abs(want)
+        mean_flx = np.mean([r["flx"] for r in full[tower.name]], axis=0)
+        mean_conc = np.mean([r["conc"] for r in full[tower.name]], axis=0)
+        assert np.abs(agg[tower.name]["flx"] - mean_flx).max() <= 1e-15 * np.abs(mean_flx).max()
+        assert np.abs(agg[tower.name]["conc"] - mean_conc).max() <= 1e-15 * np.abs(mean_conc).max()
+        omean = np.mean([_oracle_result(oracle, cfg, tower, mi)[2] for mi in range(4)], axis=0)
+        assert rel_l2(agg[tower.name]["flx"], omean) <= 1e-10
+        assert agg[tower.name]["n"] == 4

@@ -54,6 +54,49 @@ def test_sharded_world1_equals_plain(gpu_lib):
         assert np.abs(f2 - f1).max() <= 1e-12 * np.abs(f1).max()
 
 
+@pytest.mark.parametrize("G", [2, 4, 8])
+def test_emulated_ranks_equal_plain_bitwise(gpu_lib, G):
+    """The G rank programs (stage 1 -> exchange -> stage 2) run back to back on this one GPU: same kernels
+    and launch geometry per rank as a real G-GPU run, so equality here pins the ky-slab decomposition itself
+    on a single-GPU box; the NCCL / peer-store transport is what test_sharded_world2_* adds."""
+    import bldfm_b200
+    from bldfm_b200.sharded import solve_sharded_emulated
+    for footprint in (True, False):
+        kw = _problem(n=96, footprint=footprint)
+        _, c0, f0 = bldfm_b200.steady_state_transport_solver(**kw)
+        kw.pop("precision")
+        c1, f1 = solve_sharded_emulated(G, **kw)
+        assert np.array_equal(c0, c1) and np.array_equal(f0, f1), (G, footprint)
+    # uneven row blocks and truncated modes: 66 modes -> 34 half-plane rows; 8 ranks -> blocks of 5 (last: 4)
+    kw = _problem(n=96)
+    kw["modes"] = (48, 66)
+    _, c0, f0 = bldfm_b200.steady_state_transport_solver(**kw)
+    kw.pop("precision")
+    c1, f1 = solve_sharded_emulated(G, **kw)
+    assert np.array_equal(c0, c1) and np.array_equal(f0, f1), G
+
+
+def test_baseline_config5_replica_2048_sharded_against_oracle(gpu_lib, oracle):
+    """BASELINE config 5 at the 2048^2 replica SURVEY.md 8(d) allows (same dx = 7.8 m and largest wavenumber
+    as the 4096^2 x 256 case, n = 256 -> 414 levels): the 8-rank ky-slab decomposition against the oracle
+    (<= 1e-10 rel-L2) and bitwise against the unsharded solve."""
+    import bldfm_b200
+    from bldfm_b200.pbl_model import vertical_profiles
+    from bldfm_b200.sharded import solve_sharded_emulated
+    from conftest import rel_l2
+    n, nz = 2048, 256
+    dom = 32000.0 * n / 4096
+    z, prof = vertical_profiles(nz, 10.0, (-3.0, -4.0), ustar=0.4, mol=-50.0)
+    kw = dict(srf_flx=np.zeros((n, n)), z=z, profiles=prof, domain=(dom, dom), levels=nz, modes=(n, n),
+              meas_pt=(dom / 2, dom / 2), footprint=True)
+    c1, f1 = solve_sharded_emulated(8, **kw)
+    _, c0, f0 = bldfm_b200.steady_state_transport_solver(precision="double", **kw)
+    assert np.array_equal(c0, c1) and np.array_equal(f0, f1)
+    _, oc, of = oracle.solve(precision="double", nthreads=oracle.max_threads(), **kw)
+    assert rel_l2(c1, oc) <= 1e-10 and rel_l2(f1, of) <= 1e-10
+    assert abs(f1.sum() - of.sum()) <= 1e-12 * abs(of.sum())
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
