@@ -13,12 +13,22 @@ weak scaling); time = max over ranks; value = N*K / time.
   e2e       same metric through the public Python API `steady_state_transport_solver` with host
             numpy inputs/outputs (H2D of the staged profiles, D2H of conc+flx inside the timing).
   roofline  the dominant kernel (fused march): 86 flops per marched mode-step (the
-            kernel marches the conjugate-symmetric half of the M modes) / measured kernel time, against the FP64 pipe rate measured in this run by a DADD/DMUL (exact
-            mode) or DFMA (fma mode) micro-benchmark; the HBM view is given alongside.
-  cpu_baseline  the oracle port (C march with all host threads + scipy.fft) on the same config.
+            kernel marches the conjugate-symmetric half of the M modes) / measured kernel time, against the
+            FP64 pipe rate measured in this run by a DADD/DMUL (exact mode) or DFMA (fma mode)
+            micro-benchmark; the HBM view is given alongside.  `roofline_backtransform` is the second
+            kernel family (pruned real-output back-transform) against the HBM roofline in its throughput
+            regime (128 fields per launch).
+  cpu_baseline  the reference's own CPU path (staged copy under oracle/_ref, `kind: "reference"`): numba
+            march with all host threads (latency mode) and `run_bldfm_parallel(max_workers=cores)` (pool
+            mode), whichever is faster; `cpu_baseline_port` is the oracle's pthread C restatement.
+  configs   the other BASELINE configs, outside the headline timing, each with a parity flag (a false flag
+            fails the run with rc 1):  config3 (1024^2 x 129 levels, N = 1 only),  config4 (8 towers x 1440
+            met steps through `run_bldfm_parallel` with the final gather INSIDE the timing, plus the
+            measure / aggregate / device-resident variants; strong scaling on the fixed 11 520 footprints),
+            config5 (4096^2 x 256 ky-slab sharded over the N GPUs -- NCCL and fused peer-store exchange --
+            bitwise against the unsharded solve, and a 2048^2 replica against the oracle).
 
-`--impl reference` times that CPU port alone (the reference itself is pure Python + numba and is
-not available on the GPU box).
+`--impl reference` times the reference's own CPU implementation alone.
 """
 
 from __future__ import annotations
@@ -130,27 +140,77 @@ def cpu_reference_leg(kw, steps, warmup, nthreads):
     return steps / dt, dt / steps * 1e3
 
 
+def reference_cpu_leg(steps, warmup):
+    """The reference's OWN CPU path on config 2, from the staged copy under oracle/_ref, in a child process
+    (oracle/reference_runner.py): numba march with all host threads (latency mode) and the process pool of
+    run_bldfm_parallel(max_workers=cores) (pool mode).  Returns None when the copy is not staged."""
+    runner = ROOT / "oracle" / "reference_runner.py"
+    if not (ROOT / "oracle" / "_ref" / "src" / "bldfm" / "solver.py").exists():
+        return None
+    cores = len(os.sched_getaffinity(0))
+    out = {"cores": cores}
+    scratch = ROOT / "gpurun_out" / "_ref_scratch"          # the reference writes logs/, plots/ relative to cwd
+    scratch.mkdir(parents=True, exist_ok=True)
+    for mode, extra in (("latency", ["--reps", str(max(2, min(steps, 12))), "--warmup", str(max(1, min(warmup, 2)))]),
+                        ("throughput", ["--reps", "1", "--warmup", "0", "--tasks", str(2 * cores)])):
+        try:
+            r = subprocess.run([sys.executable, str(runner), "--mode", mode, "--cores", str(cores), *extra],
+                               capture_output=True, text=True, timeout=900, cwd=str(scratch))
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            out[mode] = json.loads(line[-1]) if line else {"error": (r.stderr or "no output")[-400:]}
+        except (subprocess.TimeoutExpired, OSError, ValueError) as e:
+            out[mode] = {"error": repr(e)[:400]}
+    rates = {m: out[m].get("solves_per_s", 0.0) for m in ("latency", "throughput")}
+    best = max(rates, key=rates.get)
+    if rates[best] <= 0.0:
+        return None
+    out["best_mode"] = best
+    out["solves_per_s"] = rates[best]
+    return out
+
+
+def cpu_baseline_entries(steps, warmup, kw, port_steps=40):
+    """(cpu_baseline, cpu_baseline_port): the reference itself when staged (kind "reference"), the oracle's C
+    restatement always (kind "port")."""
+    from oracle import bldfm_oracle as O
+
+    cores = O.max_threads()
+    sps, ms = cpu_reference_leg({**kw}, port_steps, 2, cores)
+    port = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "ms_per_step": ms,
+            "sample": f"{port_steps} full config-2 solves (oracle port: pthread C march + scipy.fft, all host threads)"}
+    ref = reference_cpu_leg(steps, warmup)
+    if ref is None:
+        return port, port
+    lat, thr = ref["latency"], ref["throughput"]
+    base = {"value": ref["solves_per_s"], "unit": UNIT, "cores": ref["cores"], "kind": "reference",
+            "best_mode": ref["best_mode"],
+            "sample": (f"the unmodified reference (oracle/_ref) on config 2: latency mode = "
+                       f"{lat.get('reps')} warm steady_state_transport_solver calls with NUM_THREADS={ref['cores']} "
+                       f"({lat.get('solves_per_s', 0):.3g} solves/s); pool mode = run_bldfm_parallel(max_workers="
+                       f"{ref['cores']}, parallel_over='both') over {thr.get('tasks_per_rep')} solves x {thr.get('reps')} "
+                       f"({thr.get('solves_per_s', 0):.3g} solves/s); FFT = scipy.fft in place of pyFFTW"),
+            "latency_mode": lat, "pool_mode": thr}
+    return base, port
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    from oracle import bldfm_oracle as O
-
-    O.build()
     kw = config2()
-    cores = O.max_threads()
-    steps = max(1, min(args.steps, 60))       # bounded: ~0.1 s per solve on 16 cores
+    steps = max(1, min(args.steps, 12))
     warm = max(1, min(args.warmup, 3))
-    sps, ms = cpu_reference_leg(kw, steps, warm, cores)
+    base, port = cpu_baseline_entries(steps, warm, kw, port_steps=max(5, min(args.steps, 40)))
+    from oracle import bldfm_oracle as O
     g = O.geometry(kw["srf_flx"].shape, kw["domain"], kw["modes"], None)
     mode_levels = (g["nlx"] * g["nly"] - 1) * (len(kw["z"]) - 1)
-    sample = f"{steps} full config-2 solves (oracle port: pthread C march x{cores} + scipy.fft workers={cores})"
+    sps = base["value"]
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 / sps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD},
         "mode_levels_per_s": sps * mode_levels,
-        "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": base, "cpu_baseline_port": port,
         "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -163,6 +223,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="problems per launch for the extra batched figure")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-configs", action="store_true", help="skip the config 3/4/5 legs (headline only)")
+    ap.add_argument("--c4-steps", type=int, default=1440, help="met steps of the config-4 leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -336,6 +398,31 @@ def main():
     e2e_batched_s = time.perf_counter() - tb0
     barrier()
 
+    # ---- the other BASELINE configs (outside the headline timing), every rank takes part
+    configs = {}
+    if not args.skip_configs:
+        from scripts import bench_legs
+
+        # free the headline's buffers first: config 5 wants its gigabytes
+        del bout_c, bout_f, held
+        gc.collect()
+
+        def oracle_check(kw5, c, f):
+            # the oracle as the CHECKER of the sharded replica (never timed, never on the product path)
+            from oracle import bldfm_oracle as O
+            O.build()
+            _, oc, of = O.solve(nthreads=O.max_threads(), **kw5)
+            rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))      # noqa: E731
+            return [rel(c, oc), rel(f, of)]
+
+        dist_mod = dist if world > 1 else None
+        if world == 1:
+            configs["config3"] = bench_legs.leg_config3(torch, local)
+        configs["config5"] = bench_legs.leg_config5(torch, dist_mod, rank, world, local, oracle_check=oracle_check)
+        configs["config4"] = bench_legs.leg_config4(torch, dist_mod, rank, world, local, T=args.c4_steps,
+                                                    oracle_check=oracle_check)
+        bldfm_b200.config.DEVICE = local
+
     # ---- reduce over ranks (max time)
     t = torch.tensor([dev_ms, e2e_s * 1e3, march_ms, batch_ms, e2e_batched_s * 1e3], dtype=torch.float64,
                      device=f"cuda:{local}")
@@ -407,16 +494,18 @@ def main():
                             "api": "bldfm_b200.solve_batched(wait=False) + synchronize(): pinned host results, "
                                    "D2H of a chunk overlaps the next chunk's kernels"},
         }
+        if configs:
+            line["configs"] = configs
         if not args.no_cpu and world == 1:
-            from oracle import bldfm_oracle as O
-            cores = O.max_threads()
-            sps, ms = cpu_reference_leg({**kw}, 60, 2, cores)
-            line["cpu_baseline"] = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "60 full config-2 solves (oracle port: pthread C march + scipy.fft, all host threads)",
-                                    "ms_per_step": ms}
+            line["cpu_baseline"], line["cpu_baseline_port"] = cpu_baseline_entries(6, 1, kw)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    # a false parity flag in any config leg fails the run
+    bad = [name for name, c in configs.items() if not c.get("ok", c.get("parity", {}).get("ok", True))]
+    if bad:
+        print(f"bench.py: parity flag false in {bad}", file=sys.stderr)
+        sys.exit(1)
 
 
 if __name__ == "__main__":

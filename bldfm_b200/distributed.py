@@ -123,8 +123,6 @@ class SharedResults:
     # ---- creation / reuse -------------------------------------------------------------------------
     @classmethod
     def acquire(cls, item_shape, counts):
-        import torch.distributed as dist
-
         rank, ws = world()
         key = (ws, tuple(int(s) for s in item_shape), tuple(int(c) for c in counts))
         msg = [None]
@@ -135,7 +133,9 @@ class SharedResults:
             else:
                 fd = _anon_file(2 * int(np.sum(counts)) * int(np.prod(item_shape)) * 8)
                 msg = [("new", os.getpid(), fd)]
-        dist.broadcast_object_list(msg, src=0)
+        if ws > 1:
+            import torch.distributed as dist
+            dist.broadcast_object_list(msg, src=0)
         kind, pid, cfd = msg[0]
         seg = cls._cache.get(key)
         if kind == "reuse" and seg is not None and (seg.creator_pid, seg.creator_fd) == (pid, cfd):
@@ -146,7 +146,7 @@ class SharedResults:
             fd = os.open(f"/proc/{pid}/fd/{cfd}", os.O_RDWR)
         seg = cls(item_shape, counts, rank, ws, fd, pid, cfd)
         cls._cache[key] = seg        # a still-referenced older segment stays alive through its arrays
-        dist.barrier()               # nobody writes before every rank has mapped the file
+        seg.barrier()                # nobody writes before every rank has mapped the file
         return seg
 
     def _register(self):
@@ -199,9 +199,10 @@ class SharedResults:
         return a[0], a[1]
 
     def barrier(self):
-        import torch.distributed as dist
+        if self.ws > 1:
+            import torch.distributed as dist
 
-        dist.barrier()
+            dist.barrier()
 
 
 def _anon_file(nbytes: int) -> int:

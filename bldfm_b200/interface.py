@@ -121,14 +121,6 @@ def run_bldfm_single(config, tower, met_index: int = 0, surface_flux=None, cache
 # batched core
 # ------------------------------------------------------------------------------------------------
 
-def _as_task(config, task):
-    """(tower object, met index) from either (tower index, met index) or (tower object, met index)."""
-    t, mi = task
-    if isinstance(t, (int, np.integer)):
-        t = config.towers[int(t)]
-    return t, int(mi)
-
-
 def plan_tasks(config, tasks: Sequence[Tuple[object, int]]):
     """Group tasks (tower | tower index, met index) by march key (z_m, met index).
 
@@ -136,27 +128,36 @@ def plan_tasks(config, tasks: Sequence[Tuple[object, int]]):
     """
     keys: Dict[Tuple[float, int], int] = {}
     task_group = []
-    for task in tasks:
-        tower, mi = _as_task(config, task)
-        k = (float(tower.z_m), mi)
-        task_group.append(keys.setdefault(k, len(keys)))
+    towers = config.towers
+    for t, mi in tasks:
+        if isinstance(t, (int, np.integer)):
+            t = towers[t]
+        task_group.append(keys.setdefault((float(t.z_m), int(mi)), len(keys)))
     return list(keys.keys()), task_group
 
 
 class TaskBatch:
     """The pending tasks of one call, prepared for the device without per-task Python work: one
-    ``ProfileBatch`` row per march group, one ``bldfm_problem`` per task, chunk boundaries on group edges."""
+    ``ProfileBatch`` row per march group, one ``bldfm_problem`` per task.
+
+    The profiles are computed lazily in blocks of ``BLOCK`` march groups (one vectorised
+    ``vertical_profiles_batch`` call each), so that only the first block's host work is exposed: the
+    launches are enqueue-only, and the following blocks are prepared while the device works.
+    """
+
+    BLOCK = 128
 
     def __init__(self, config, tasks):
         self.config = config
-        self.tasks = [_as_task(config, t) for t in tasks]
+        towers = config.towers
+        self.tasks = [(towers[t] if isinstance(t, (int, np.integer)) else t, int(mi)) for t, mi in tasks]
         self.keys, self.task_group = plan_tasks(config, self.tasks)
+        self.task_group = np.asarray(self.task_group, dtype=np.int64)
+        self.xm = np.array([t.x for t, _ in self.tasks], dtype=np.float64)
+        self.ym = np.array([t.y for t, _ in self.tasks], dtype=np.float64)
         self.steps = {}
-        for _, mi in self.keys:
-            if mi not in self.steps:
-                self.steps[mi] = config.met.get_step(mi)
-        self.profiles = profiles_batch(config, [k[0] for k in self.keys], [self.steps[k[1]] for k in self.keys]) \
-            if self.keys else None
+        self._blocks: Dict[int, ProfileBatch] = {}
+        self.prep_seconds = 0.0
         dom, sol = config.domain, config.solver
         self.domain = (dom.xmax, dom.ymax)
         self.levels = _levels(config)
@@ -165,19 +166,48 @@ class TaskBatch:
         self.solver_kw = dict(domain=self.domain, levels=self.levels, modes=dom.modes, footprint=sol.footprint,
                               analytic=sol.analytic, halo=dom.halo, precision=sol.precision)
 
+    def step(self, mi):
+        s = self.steps.get(mi)
+        if s is None:
+            s = self.steps[mi] = self.config.met.get_step(mi)
+        return s
+
+    def _block(self, b) -> ProfileBatch:
+        pb = self._blocks.get(b)
+        if pb is None:
+            import time
+            t0 = time.perf_counter()
+            keys = self.keys[b * self.BLOCK:(b + 1) * self.BLOCK]
+            pb = profiles_batch(self.config, [k[0] for k in keys], [self.step(k[1]) for k in keys])
+            self._blocks[b] = pb
+            self.prep_seconds += time.perf_counter() - t0
+        return pb
+
     def problems(self, idx):
         """bldfm_problem array (+ keepalive) for the tasks ``idx`` (indices into self.tasks)."""
-        xm = np.array([self.tasks[t][0].x for t in idx], dtype=np.float64)
-        ym = np.array([self.tasks[t][0].y for t in idx], dtype=np.float64)
-        rows = np.array([self.task_group[t] for t in idx], dtype=np.int64)
-        return _lib.problems_from_batch(self.profiles, rows, xm, ym, 0.0)
+        idx = np.asarray(idx, dtype=np.int64)
+        groups = self.task_group[idx]
+        blocks = groups // self.BLOCK
+        b0 = int(blocks[0]) if len(blocks) else 0
+        if len(blocks) == 0 or bool((blocks == b0).all()):
+            return _lib.problems_from_batch(self._block(b0), groups - b0 * self.BLOCK, self.xm[idx], self.ym[idx], 0.0)
+        # the chunk spans blocks: the structs hold absolute addresses, so the pieces simply concatenate
+        arr = np.zeros(len(idx), dtype=_lib.PROBLEM_DTYPE)
+        keep = []
+        for b in np.unique(blocks):
+            sel = np.nonzero(blocks == b)[0]
+            part, k = _lib.problems_from_batch(self._block(int(b)), groups[sel] - int(b) * self.BLOCK,
+                                               self.xm[idx[sel]], self.ym[idx[sel]], 0.0)
+            arr[sel] = part
+            keep.append(k)
+        return arr, (arr, keep)
 
     def is_f32(self):
         """Per task: float32 fields in the reference (precision="single", no phase shift)?"""
         sol = self.config.solver
         if sol.precision == "double" or sol.footprint:
             return np.zeros(len(self.tasks), dtype=bool)
-        return np.array([not (t.x * t.x + t.y * t.y > 0.0) for t, _ in self.tasks], dtype=bool)
+        return ~(self.xm * self.xm + self.ym * self.ym > 0.0)
 
     def chunks(self, idx, per_task_bytes):
         """Split the task indices ``idx`` into launches of at most MAX_CHUNK_BYTES / 256 problems."""
@@ -185,7 +215,8 @@ class TaskBatch:
         return [idx[c0:c0 + chunk] for c0 in range(0, len(idx), chunk)]
 
     def row(self, t):
-        return self.profiles.row(self.task_group[t])
+        g = int(self.task_group[t])
+        return self._block(g // self.BLOCK).row(g % self.BLOCK)
 
 
 def solve_tasks(config, tasks: Sequence[Tuple[object, int]], surface_flux=None, cache=None, out=None,
@@ -207,7 +238,7 @@ def solve_tasks(config, tasks: Sequence[Tuple[object, int]], surface_flux=None, 
             z, profiles = tb.row(t)
             hit = cache.get(z, profiles, domain, dom.modes, (tower.x, tower.y), dom.halo, sol.precision)
             if hit is not None:
-                results[t] = _result(tower, tb.steps[mi], *hit)
+                results[t] = _result(tower, tb.step(mi), *hit)
                 continue
         pending.append(t)
 
@@ -239,7 +270,7 @@ def solve_tasks(config, tasks: Sequence[Tuple[object, int]], surface_flux=None, 
             res = (grid, np.squeeze(conc[b]), np.squeeze(flx[b]))
             if cache is not None and sol.footprint:                   # solver.py:301-302
                 cache.put(z, profiles, domain, dom.modes, (tower.x, tower.y), dom.halo, sol.precision, *res)
-            results[t] = _result(tower, tb.steps[mi], *res)
+            results[t] = _result(tower, tb.step(mi), *res)
     return results
 
 
@@ -290,7 +321,7 @@ def run_bldfm_parallel(config, max_workers=None, parallel_over: str = "towers", 
     (``distributed.SharedResults``): the final gather is that segment plus one barrier -- no field crosses a
     PCIe link twice and none goes through another GPU.  Rank 0 returns the full result dict (arrays are views
     into the segment), the other ranks an empty dict; ``gather=False`` returns each rank's own share.
-    Without a process group this is ``run_bldfm_multitower`` on one GPU.
+    Without a process group the same path runs with one rank (a page-locked segment of this process).
     ``max_workers`` and ``parallel_over`` are accepted for compatibility; the strategies differ only
     in how the reference slices its task list, the results are identical (tests/test_parallel.py:78-90).
     """
@@ -300,10 +331,6 @@ def run_bldfm_parallel(config, max_workers=None, parallel_over: str = "towers", 
         logger.warning("surface_flux is ignored in parallel mode; an ideal source is generated "
                        "(interface.py:270-275).")
         surface_flux = None
-    rank, ws = _dist.world()
-    if ws == 1:
-        return run_bldfm_multitower(config)
-
     n = config.met.n_timesteps
     towers = config.towers
     tasks = _multitower_tasks(config)
@@ -344,7 +371,7 @@ def run_bldfm_parallel(config, max_workers=None, parallel_over: str = "towers", 
         c, f = np.squeeze(conc_all[pos[t]]), np.squeeze(flx_all[pos[t]])
         if is32[t]:
             c, f = c.astype(np.float32), f.astype(np.float32)
-        out[tower.name][mi] = _result(tower, tb.steps[mi], grid, c, f)
+        out[tower.name][mi] = _result(tower, tb.step(mi), grid, c, f)
     return out
 
 

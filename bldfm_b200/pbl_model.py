@@ -32,8 +32,14 @@ def psi(x):
     """Integrated Businger-Dyer stability correction for momentum (pbl_model.py:207-230)."""
     x = np.asarray(x, dtype=np.float64)
     stable = x > 0.0
-    # (1-16x)^(1/4) through the complex power like the reference, real part taken
-    xi = np.where(stable, np.nan, np.power(1.0 - 16.0 * x, 0.25, dtype=complex).real)
+    # (1-16x)^(1/4) through the complex power like the reference, real part taken -- evaluated only where
+    # it is used (elementwise, so the values are the same; the complex power is the expensive part)
+    xi = np.full(x.shape, np.nan)
+    if x.ndim == 0:
+        if not stable:
+            xi = np.power(1.0 - 16.0 * x, 0.25, dtype=complex).real
+    else:
+        xi[~stable] = np.power(1.0 - 16.0 * x[~stable], 0.25, dtype=complex).real
     unstable_val = (
         -2.0 * np.log(0.5 * (1.0 + xi))
         - np.log(0.5 * (1.0 + xi**2))
@@ -46,7 +52,12 @@ def psi(x):
 def phi(x):
     """Businger-Dyer stability function for the eddy diffusivity (pbl_model.py:233-250)."""
     x = np.asarray(x, dtype=np.float64)
-    return np.where(x > 0.0, 1.0 + 5.0 * x, np.power(1.0 - 16.0 * x, -0.5, dtype=complex).real)
+    stable = x > 0.0
+    if x.ndim == 0:
+        return np.where(stable, 1.0 + 5.0 * x, np.power(1.0 - 16.0 * x, -0.5, dtype=complex).real)
+    out = 1.0 + 5.0 * x
+    out[~stable] = np.power(1.0 - 16.0 * x[~stable], -0.5, dtype=complex).real
+    return out
 
 
 def _surface_layer(closure, zm, absum, ustar, z0, mol, tke):
