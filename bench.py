@@ -66,7 +66,9 @@ WORKLOAD = ("BASELINE config 2: single-tower footprint 512x512, n=64 (105 levels
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of k_march on this workload, from the committed
 # `ncu --set full` captures under profiles/ (key: march mode, full-plane march)
-NCU_TRAFFIC = {("exact", True): 84736, ("exact", False): 90112}
+NCU_TRAFFIC = {("exact", True): 84736, ("exact", False): 90112, ("fma", False): 80640}
+# same for the back-transform pair in its throughput regime (128 fields): profiles/r1i_fft24_batched_ncu.txt
+NCU_TRAFFIC_BT = 998365184
 
 
 class ClockSampler:
@@ -262,12 +264,13 @@ def main():
     M = geom.nlx * geom.nly - 1
     S = len(kw["z"]) - 1
     mode_levels = M * S
-    fma_mode = bldfm_b200.config.MARCH_MODE == "fma"
-    flags = _lib.FOOTPRINT | _lib.DOUBLE | _lib.OUT_ON_DEVICE | _lib.ASYNC | (_lib.MARCH_FMA if fma_mode else 0)
+    base_flags = _lib.FOOTPRINT | _lib.DOUBLE | _lib.OUT_ON_DEVICE | _lib.ASYNC
     if bldfm_b200.config.FFT_LIBRARY:
-        flags |= _lib.FFT_LIBRARY
+        base_flags |= _lib.FFT_LIBRARY
     if bldfm_b200.config.MARCH_FULL:
-        flags |= _lib.MARCH_FULL
+        base_flags |= _lib.MARCH_FULL
+    mode_flag = {"exact": 0, "fma": _lib.MARCH_FMA, "auto": _lib.MARCH_AUTO}[bldfm_b200.config.MARCH_MODE]
+    flags = base_flags | mode_flag
 
     plan = bldfm_b200.get_fft_manager().plan(geom, local)
     stream = torch.cuda.ExternalStream(L.bldfm_plan_stream(plan), device=local)
@@ -278,16 +281,17 @@ def main():
     out_f = torch.empty_like(out_c)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
 
-    def solve_dev():
-        _lib.check(L.bldfm_solve(plan, C.byref(prob), lvp, 1, None, flags, out_c.data_ptr(), out_f.data_ptr()))
+    def solve_dev(fl=None):
+        _lib.check(L.bldfm_solve(plan, C.byref(prob), lvp, 1, None, flags if fl is None else fl,
+                                 out_c.data_ptr(), out_f.data_ptr()))
 
     def flush_l2():
         with torch.cuda.stream(stream):
             flush.zero_()
 
     # ---- FP64 pipe peak measured in this run (roofline denominator)
-    peak_ops = C.c_double(0.0)
-    _lib.check(L.bldfm_fp64_peak(local, 1 if fma_mode else 0, 20000, C.byref(peak_ops)))
+    peak_ops = C.c_double(0.0)         # non-fused DADD/DMUL issue rate (the bit-mirrored march cannot use FMAs)
+    _lib.check(L.bldfm_fp64_peak(local, 0, 20000, C.byref(peak_ops)))
     peak_fma = C.c_double(0.0)
     _lib.check(L.bldfm_fp64_peak(local, 1, 20000, C.byref(peak_fma)))
 
@@ -307,20 +311,25 @@ def main():
         barrier()
     launches = int(L.bldfm_plan_launch_count(plan)) - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    fma_mode = bool(L.bldfm_plan_last_march_mode(plan))      # what "auto" picked for this workload
 
-    # ---- kernel timing for the roofline (per-stage events inside the library)
+    # ---- kernel timing for the roofline (per-stage events inside the library), both arithmetic modes
     L.bldfm_plan_set_profiling(plan, 1)
     tm = _lib.Timings()
-    march_ms = inv_ms = 0.0
     nprof = min(args.steps, 20)
-    for _ in range(nprof):
-        flush_l2()
-        solve_dev()
-        _lib.check(L.bldfm_plan_last_timings(plan, C.byref(tm)))
-        march_ms += tm.march_ms
-        inv_ms += tm.inverse_ms
-    march_ms /= nprof
-    inv_ms /= nprof
+    march_by_mode = {}
+    inv_ms = 0.0
+    for mname, mflag in (("exact", 0), ("fma", _lib.MARCH_FMA)):
+        acc = 0.0
+        for _ in range(nprof):
+            flush_l2()
+            solve_dev(base_flags | mflag)
+            _lib.check(L.bldfm_plan_last_timings(plan, C.byref(tm)))
+            acc += tm.march_ms
+            inv_ms += tm.inverse_ms
+        march_by_mode[mname] = acc / nprof
+    inv_ms /= 2 * nprof
+    march_ms = march_by_mode["fma" if fma_mode else "exact"]
     L.bldfm_plan_set_profiling(plan, 0)
 
     # ---- end-to-end leg through the public API (host in, host out)
@@ -365,6 +374,22 @@ def main():
     for _ in range(3):
         solve_batch()
     torch.cuda.synchronize()
+    # back-transform in its throughput regime: 64 problems = 128 fields of 1536^2 -> 512^2 per launch pair
+    BT = 64
+    bt_parr = (_lib.Problem * BT)(*[probs[b % B] for b in range(BT)])
+    bt_c = torch.empty((BT, 512, 512), dtype=torch.float64, device=f"cuda:{local}")
+    bt_f = torch.empty_like(bt_c)
+    L.bldfm_plan_set_profiling(plan, 1)
+    bt_times = []
+    for i in range(8):
+        flush_l2()
+        _lib.check(L.bldfm_solve_batched(plan, BT, bt_parr, lvp, 1, None, flags, bt_c.data_ptr(), bt_f.data_ptr()))
+        _lib.check(L.bldfm_plan_last_timings(plan, C.byref(tm)))
+        if i >= 2:
+            bt_times.append(tm.inverse_ms)
+    L.bldfm_plan_set_profiling(plan, 0)
+    bt_ms = float(np.median(bt_times))
+    del bt_c, bt_f
     nb = max(3, args.steps // 4)
     bev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nb)]
     for a, b in bev:
@@ -424,11 +449,11 @@ def main():
         bldfm_b200.config.DEVICE = local
 
     # ---- reduce over ranks (max time)
-    t = torch.tensor([dev_ms, e2e_s * 1e3, march_ms, batch_ms, e2e_batched_s * 1e3], dtype=torch.float64,
+    t = torch.tensor([dev_ms, e2e_s * 1e3, march_ms, batch_ms, e2e_batched_s * 1e3, bt_ms], dtype=torch.float64,
                      device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, march_ms_max, batch_ms, e2e_batched_ms = (float(x) for x in t.tolist())
+    dev_ms, e2e_ms, march_ms_max, batch_ms, e2e_batched_ms, bt_ms = (float(x) for x in t.tolist())
 
     if rank == 0:
         value = world * args.steps / (dev_ms * 1e-3)
@@ -439,8 +464,20 @@ def main():
         M_run = M if full_march else geom.nlx * (geom.nly // 2 + 1) + (geom.nly - 1) // 2 - 1
         flops = 86.0 * M_run * S
         achieved = flops / (march_ms * 1e-3) * 1e-12
-        peak = (peak_ops.value * (2.0 if fma_mode else 1.0)) * 1e-3        # TFLOP/s
+        peak = (peak_fma.value * 2.0 if fma_mode else peak_ops.value) * 1e-3        # TFLOP/s
         alg_bytes = 2 * geom.nlx * geom.nly * 16 + S * 128
+        mode_rooflines = {}
+        for mname, mms in march_by_mode.items():
+            pk = (peak_fma.value * 2.0 if mname == "fma" else peak_ops.value) * 1e-3
+            mode_rooflines[mname] = {"kernel_ms": mms, "achieved": flops / (mms * 1e-3) * 1e-12, "peak": pk,
+                                     "unit": "TFLOP/s", "frac": flops / (mms * 1e-3) * 1e-12 / pk,
+                                     "peak_source": "bldfm_fp64_peak in this run: " +
+                                                    ("DFMA x2" if mname == "fma" else "DADD/DMUL (non-fused ops)")}
+        # back-transform, throughput regime: algorithmic bytes per field = half-plane spectrum in, intermediate
+        # written + read, real field out
+        nrow = geom.nly // 2 + 1
+        bt_bytes_field = nrow * geom.nlx * 16 + 2 * nrow * geom.nx * 16 + geom.nx * geom.ny * 8
+        bt_fields = 2 * 64
         # the HBM side of the roofline (not the binding one for this kernel): driver-measured copy bandwidth
         try:
             hbm_peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
@@ -453,6 +490,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "march_mode": bldfm_b200.config.MARCH_MODE,
+                       "march_arithmetic_used": "fma" if fma_mode else "exact",
                        "fft": "cufft" if bldfm_b200.config.FFT_LIBRARY else "auto",
                        "l2": "flushed with a 256 MiB memset between timed steps"},
             "mode_levels_per_s": value * mode_levels,
@@ -472,7 +510,8 @@ def main():
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
                 # capture of this kernel on this workload (profiles/r1a_march_exact_ncu.txt): the 8.4 MB
                 # of spectra it writes stay in the 126 MB L2 for the transform that follows
-                "traffic": NCU_TRAFFIC.get((bldfm_b200.config.MARCH_MODE, full_march)),
+                "traffic": NCU_TRAFFIC.get(("fma" if fma_mode else "exact", full_march)),
+                "arithmetic": "fma" if fma_mode else "exact", "by_mode": mode_rooflines,
                 "flops_per_launch": flops, "kernel_ms": march_ms,
                 "modes_marched": M_run, "modes_retained": M,
                 # the same launch counted with SURVEY.md 8d's figure 86*M*S (what the reference executes)
@@ -486,6 +525,19 @@ def main():
                              "frac": alg_bytes / (march_ms * 1e-3) * 1e-9 / hbm_peak},
                 "share_of_step": march_ms / (dev_ms / args.steps),
                 "inverse_ms": inv_ms,
+            },
+            "roofline_backtransform": {
+                "kernel": "k_fft24 / k_fft48 pass X + pass Y (pruned real-output back-transform, K9-K11)",
+                "regime": "128 fields (64 footprint solves) of 1536^2 -> 512^2 per launch pair",
+                "bound": "hbm", "unit": "GB/s", "achieved": bt_fields * bt_bytes_field / (bt_ms * 1e-3) * 1e-9,
+                "peak": hbm_peak, "peak_source": hbm_src,
+                "frac": bt_fields * bt_bytes_field / (bt_ms * 1e-3) * 1e-9 / hbm_peak,
+                "traffic": NCU_TRAFFIC_BT, "algorithmic_bytes": bt_fields * bt_bytes_field,
+                "kernel_ms": bt_ms, "us_per_field": bt_ms * 1e3 / bt_fields,
+                # the FP64 side: ~58 k FP64 instructions per length-1536 transform, 513 transforms per field
+                "fp64_view": {"fp64_instr_per_field_estimate": 513 * 58000,
+                              "floor_us_per_field": 513 * 58000 / (peak_ops.value * 1e9) * 1e6,
+                              "note": "on B200 the FP64 pipe (not HBM) is the tighter floor of this kernel; see DESIGN.md 3.2"},
             },
             "batched": {"batch": B, "ms_per_batch": batch_ms, "solves_per_s": world * B / (batch_ms * 1e-3),
                         "mode_levels_per_s": world * B / (batch_ms * 1e-3) * mode_levels},

@@ -51,7 +51,7 @@ EXPORTS = [
     "bldfm_march_coverage",
     "bldfm_solve_batched_accumulate", "bldfm_kappa", "bldfm_auto_kappa_limit", "bldfm_plan_last_march_mode",
     "bldfm_device_memset", "bldfm_host_register", "bldfm_host_unregister",
-    "bldfm_peer_signal", "bldfm_peer_wait", "bldfm_peer_status",
+    "bldfm_peer_signal", "bldfm_peer_wait", "bldfm_peer_status", "bldfm_plan_march_trace",
 ]
 
 
@@ -155,6 +155,7 @@ def lib():
         "bldfm_peer_signal": (C.c_int, [vp, vp, i32, C.c_uint64]),
         "bldfm_peer_wait": (C.c_int, [vp, vp, i32, C.c_uint64, dbl]),
         "bldfm_peer_status": (C.c_int, [vp, C.POINTER(i32)]),
+        "bldfm_plan_march_trace": (C.c_int, [vp, vp, i64, C.POINTER(i64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -126,6 +126,8 @@ struct bldfm_plan {
     cudaEvent_t copy_done[2] = {nullptr, nullptr};
     bool copy_pending[2] = {false, false};
     DevBuf weight, partial;  // f-4 weighted sums: weight map [ny][nx], partial sums | results
+    DevBuf march_trace;      // BLDFM_B200_MARCH_TRACE diagnostics: 4 timestamps per CTA of the last march
+    int64_t march_trace_ctas = 0;
     DevBuf peer_status;      // fused transpose: set by k_peer_wait when a peer never arrived
     Staging staging[kStagingSlots];
     int staging_next = 0;
@@ -691,6 +693,12 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         if (smem > pl->smem_optin)
             return fail(BLDFM_ERR_INVALID, "nz too large for the shared-memory coefficient table (" +
                                                std::to_string(nz_max) + " levels)");
+        static const bool want_trace = fft_env_int("BLDFM_B200_MARCH_TRACE", 0) != 0;
+        if (want_trace) {
+            TRY(pl->march_trace.ensure(sizeof(unsigned long long) * 4 * (size_t)grid.x * grid.y));
+            a.trace = static_cast<unsigned long long*>(pl->march_trace.p);
+            pl->march_trace_ctas = (int64_t)grid.x * grid.y;
+        }
         if (analytic) {
             k_analytic<<<grid, kMarchThreads, 0, pl->stream>>>(a);
         } else {
@@ -1047,7 +1055,7 @@ int bldfm_plan_destroy(bldfm_plan* pl)
     if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);
     pl->tables.release(); pl->params.release(); pl->spec_p.release(); pl->spec_q.release();
     pl->pad_in.release(); pl->pad_out.release(); pl->src_in.release(); pl->src_pad.release();
-    pl->weight.release(); pl->partial.release(); pl->peer_status.release();
+    pl->weight.release(); pl->partial.release(); pl->peer_status.release(); pl->march_trace.release();
     pl->fft_work.release(); pl->tw64.release(); pl->tw32.release(); pl->t24_64.release(); pl->t24_32.release(); pl->t48_64.release(); pl->t48_32.release(); pl->out_c.release(); pl->out_f.release();
     for (auto& s : pl->staging) {
         if (s.host) cudaFreeHost(s.host);
@@ -1239,6 +1247,19 @@ int bldfm_kappa(const bldfm_geometry* g, const bldfm_problem* prob, int32_t leve
 }
 
 double bldfm_auto_kappa_limit(void) { return auto_kappa_limit(); }
+
+int bldfm_plan_march_trace(bldfm_plan* pl, uint64_t* host, int64_t max_ctas, int64_t* nctas)
+{
+    if (!pl || !host || !nctas) return fail(BLDFM_ERR_INVALID, "NULL argument");
+    *nctas = 0;
+    if (!pl->march_trace.p) return fail(BLDFM_ERR_INVALID, "no march trace recorded (set BLDFM_B200_MARCH_TRACE=1)");
+    DeviceGuard guard(pl->device);
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    const int64_t n = std::min(max_ctas, pl->march_trace_ctas);
+    CUDA_TRY(cudaMemcpy(host, pl->march_trace.p, sizeof(uint64_t) * 4 * (size_t)n, cudaMemcpyDeviceToHost));
+    *nctas = n;
+    return BLDFM_OK;
+}
 
 int bldfm_plan_last_march_mode(const bldfm_plan* pl) { return pl ? pl->last_march_fma : 0; }
 

@@ -168,7 +168,16 @@ struct MarchArgs {
     void* outp;                // [slot][row][nly_loc][nlx] complex (double2 | float2)
     void* outq;
     int64_t slot_stride;       // complex elements between output slots (= nlv*nly_loc*nlx)
+    unsigned long long* trace; // diagnostics (BLDFM_B200_MARCH_TRACE): per CTA %globaltimer at start, after
+                               // staging, after the march loop, at the end; NULL = off
 };
+
+__device__ __forceinline__ unsigned long long march_now()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 __device__ __forceinline__ double round_f32(double x) { return (double)(float)x; }
 
@@ -181,9 +190,9 @@ struct Emit {
     double lx, ly;
     double cs0, sn0;     // phase factor of the group's first tower, hoisted out of the row loop
 
-    __device__ __forceinline__ Emit(const MarchArgs& a_, const GroupDesc& gd_, int64_t mode_,
+    __device__ __forceinline__ Emit(const MarchArgs& a_, const GroupDesc& gd_, const TowerDesc* tw_, int64_t mode_,
                                     int64_t mirror_, double lx_, double ly_)
-        : a(a_), gd(gd_), tw(a_.towers + gd_.tow_begin), mode(mode_), mirror(mirror_), lx(lx_), ly(ly_),
+        : a(a_), gd(gd_), tw(tw_), mode(mode_), mirror(mirror_), lx(lx_), ly(ly_),
           cs0(1.0), sn0(0.0)
     {
         if (gd.tow_count > 0 && tw[0].shift) phase(tw[0], cs0, sn0);
@@ -303,30 +312,24 @@ __host__ __device__ __forceinline__ bool march_map(const MarchArgs& a, int64_t t
 
 constexpr int kMarchThreads = 128;
 
-// grid = (ceil(nlx*nly / kMarchThreads), ngroups) ; dynamic smem = coef_stride*128 + nrow_of*4
-template <bool FMA, bool MULTI>
-__global__ void __launch_bounds__(kMarchThreads, 7)
-k_march(const MarchArgs a)
+// The per-level table of the march, staged once per CTA in shared memory from the per-solve parameter buffer.
+// (Measured alternative, round 2: the table carried in the kernel's parameter space and read with
+// warp-uniform LDC inside the loop -- no H2D copy, no staging, no barrier -- is 14 % (exact) to 36 % (fma)
+// SLOWER at config 2: the constant-bank loads do not keep up with 8 broadcast LDS.128 per step.)
+struct SmemCoef {
+    const LevelCoef* sc;
+    const int32_t* srow;
+    __device__ __forceinline__ const LevelCoef& operator[](int i) const { return sc[i]; }
+    __device__ __forceinline__ int row(int i, const MarchArgs&) const { return srow[i]; }
+};
+
+template <bool FMA, bool MULTI, class Coef>
+__device__ __forceinline__ void march_body(const MarchArgs& a, const GroupDesc& gd, const TowerDesc* towers,
+                                           const Coef& sc, int64_t tid)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    LevelCoef* sc = reinterpret_cast<LevelCoef*>(smem_raw);
-    int32_t* srow = reinterpret_cast<int32_t*>(sc + a.coef_stride);
-
-    // the back-transform that follows may be launched as soon as every CTA of this grid is resident; its
-    // CTAs start when ours retire and wait for the spectra in cudaGridDependencySynchronize()
-    cudaTriggerProgrammaticLaunchCompletion();
-    const GroupDesc gd = a.groups[blockIdx.y];
     const int S = gd.S;
-    {
-        const double2* src = reinterpret_cast<const double2*>(a.coef + (size_t)blockIdx.y * a.coef_stride);
-        double2* dst = reinterpret_cast<double2*>(sc);
-        for (int i = threadIdx.x; i < S * 8; i += kMarchThreads) dst[i] = src[i];
-        for (int i = threadIdx.x; i < a.nrow_of; i += kMarchThreads) srow[i] = a.row_of[i];
-    }
-    __syncthreads();
-
     ModeMap mm;
-    if (!march_map(a, (int64_t)blockIdx.x * kMarchThreads + threadIdx.x, mm)) return;
+    if (!march_map(a, tid, mm)) return;
     const int kx = mm.kx, ky = mm.ky;
     const double lx = a.lx[kx], ly = a.ly[ky];
 
@@ -342,21 +345,22 @@ k_march(const MarchArgs a)
         q0r = sv.x * a.src_scale; q0i = sv.y * a.src_scale;
     }
 
-    const Emit emit(a, gd, mm.mode, mm.mirror, lx, ly);
+    const Emit emit(a, gd, towers, mm.mode, mm.mirror, lx, ly);
 
     if (ky == 0 && kx == 0) {
         // degenerate mode: flux constant, concentration by the trapezoid rule (solver.py:190-191,239-251)
         double pr = gd.p000, pi = 0.0;
         bool any = false;
         for (int i = 0; i < S; ++i) {
-            if (srow[i] >= 0) { emit(srow[i], pr, pi, q0r, q0i); any = true; }
+            const int r = sc.row(i, a);
+            if (r >= 0) { emit(r, pr, pi, q0r, q0i); any = true; }
             pr = pr - (q0r * sc[i].h) * sc[i].w;
             pi = pi - (q0i * sc[i].h) * sc[i].w;
         }
-        if (srow[S] >= 0) { emit(srow[S], pr, pi, q0r, q0i); any = true; }
+        if (sc.row(S, a) >= 0) { emit(sc.row(S, a), pr, pi, q0r, q0i); any = true; }
         // rows never visited keep tfftp[0,0,0]=p000 (row 0) / 0 and tfftq[:,0,0]=tfftq0[0,0]
         int visited = 0;
-        for (int i = 0; i <= S; ++i) visited += (srow[i] >= 0);
+        for (int i = 0; i <= S; ++i) visited += (sc.row(i, a) >= 0);
         for (int r = visited; r < a.nlv; ++r)
             emit(r, (r == 0 && !any) ? gd.p000 : 0.0, 0.0, q0r, q0i);
         return;
@@ -399,6 +403,7 @@ k_march(const MarchArgs a)
             apply<FMA>(P, p2r, p2i, q2r, q2i);
         }
     }
+    if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 2] = march_now();
 
     // radiation condition at the top: eig, alpha (solver.py:164-174, 228-230)
     double alr, ali;
@@ -430,7 +435,7 @@ k_march(const MarchArgs a)
         const int last = a.last_level < S ? a.last_level : S;
         int rows = 0;
         for (int i = 0; i <= last; ++i) {
-            const int row = srow[i];
+            const int row = sc.row(i, a);
             if (row >= 0) {
                 double mr, mi, pr, pi, qr, qi;
                 cmul_np(alr, ali, p1r, p1i, mr, mi); pr = mr + p2r; pi = mi + p2i;
@@ -446,6 +451,33 @@ k_march(const MarchArgs a)
         }
         for (int r = rows; r < a.nlv; ++r) emit(r, 0.0, 0.0, 0.0, 0.0);
     }
+}
+
+// grid = (ceil(nthreads / kMarchThreads), ngroups) ; dynamic smem = coef_stride*128 + nrow_of*4
+template <bool FMA, bool MULTI>
+__global__ void __launch_bounds__(kMarchThreads, 7)
+k_march(const MarchArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LevelCoef* sc = reinterpret_cast<LevelCoef*>(smem_raw);
+    int32_t* srow = reinterpret_cast<int32_t*>(sc + a.coef_stride);
+
+    // the back-transform that follows may be launched as soon as every CTA of this grid is resident; its
+    // CTAs start when ours retire and wait for the spectra in cudaGridDependencySynchronize()
+    cudaTriggerProgrammaticLaunchCompletion();
+    if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 0] = march_now();
+    const GroupDesc gd = a.groups[blockIdx.y];
+    {
+        const double2* src = reinterpret_cast<const double2*>(a.coef + (size_t)blockIdx.y * a.coef_stride);
+        double2* dst = reinterpret_cast<double2*>(sc);
+        for (int i = threadIdx.x; i < gd.S * 8; i += kMarchThreads) dst[i] = src[i];
+        for (int i = threadIdx.x; i < a.nrow_of; i += kMarchThreads) srow[i] = a.row_of[i];
+    }
+    __syncthreads();
+    if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 1] = march_now();
+    march_body<FMA, MULTI>(a, gd, a.towers + gd.tow_begin, SmemCoef{sc, srow},
+                           (int64_t)blockIdx.x * kMarchThreads + threadIdx.x);
+    if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 3] = march_now();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -469,7 +501,7 @@ k_analytic(const MarchArgs a)
         const double2 sv = a.src_spec[(size_t)(wy - a.src_ky0) * a.src_pitch + wx];
         q0r = sv.x * a.src_scale; q0i = sv.y * a.src_scale;
     }
-    const Emit emit(a, gd, mm.mode, mm.mirror, lx, ly);
+    const Emit emit(a, gd, a.towers + gd.tow_begin, mm.mode, mm.mirror, lx, ly);
     const double h = gd.h_analytic;
     if (ky == 0 && kx == 0) {
         // tfftp[:,0,0] = p000 - tfftq0[0,0]*Kzinv*h ; tfftq[:,0,0] = tfftq0[0,0]

@@ -39,7 +39,8 @@ def _make_cache(config):
     if config.parallel.use_cache and config.solver.footprint:
         from .cache import GreensFunctionCache
 
-        return GreensFunctionCache()
+        # the batched drivers produce entries far faster than np.savez writes them: write behind
+        return GreensFunctionCache(background=True)
     return None
 
 

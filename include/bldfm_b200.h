@@ -121,6 +121,9 @@ int64_t bldfm_plan_launch_count(const bldfm_plan *plan);
 /* enable (1) / disable (0) per-stage event timing; read the last solve's numbers (synchronises) */
 int  bldfm_plan_set_profiling(bldfm_plan *plan, int enabled);
 int  bldfm_plan_last_timings(bldfm_plan *plan, bldfm_timings *out);
+/* diagnostics: with BLDFM_B200_MARCH_TRACE=1 in the environment the march kernel records four %globaltimer
+ * stamps per CTA (start, tables staged, march loop done, end); copies up to max_ctas x 4 of the last march */
+int  bldfm_plan_march_trace(bldfm_plan *plan, uint64_t *host, int64_t max_ctas, int64_t *nctas);
 /* bytes of device workspace currently held by the plan */
 int64_t bldfm_plan_workspace_bytes(const bldfm_plan *plan);
 

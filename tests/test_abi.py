@@ -123,3 +123,25 @@ def test_march_thread_map_covers_every_mode_once(L, shape, modes, halo):
     assert cover(0, g.nly, 0, count) == g.nlx * g.nly and (count == 1).all()
     with pytest.raises(ValueError):
         cover(0, nrow + 1, 1, count)
+
+
+def test_kappa_matches_the_oracle_formula(L, oracle):
+    """bldfm_kappa (host arithmetic behind BLDFM_MARCH_AUTO) == SURVEY.md Appendix C's conditioning number as
+    the oracle computes it, on every golden case; the default gate is 8.5."""
+    import ctypes as C
+    from bldfm_b200 import _lib
+    from conftest import SOLVE_CASES, load_case
+    lib = L.lib()
+    assert abs(lib.bldfm_auto_kappa_limit() - 8.5) < 1e-12 or "BLDFM_B200_AUTO_KAPPA" in __import__("os").environ
+    for name in SOLVE_CASES:
+        kw, _ = load_case(name)
+        shape = np.asarray(kw["srf_flx"]).shape
+        g = oracle.geometry(shape, kw["domain"], kw["modes"], kw.get("halo"))
+        geom = _lib.geometry(shape, kw["domain"], kw["modes"], kw.get("halo"))
+        z = np.asarray(kw["z"], dtype=np.float64)
+        lvl = int(np.max(np.atleast_1d(kw["levels"])))
+        prob, keep = _lib.make_problem(z, kw["profiles"], (0.0, 0.0), 0.0)
+        kap = C.c_double(0.0)
+        assert lib.bldfm_kappa(C.byref(geom), C.byref(prob), lvl, C.byref(kap)) == 0
+        want = oracle.kappa(z, [np.asarray(p, dtype=np.float64) for p in kw["profiles"]], g, float(z[lvl]))
+        assert abs(kap.value - want) <= 1e-9 * max(1.0, abs(want)), name

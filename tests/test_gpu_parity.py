@@ -53,11 +53,11 @@ def test_ivp_bitwise_against_oracle_random(B, oracle):
 def test_ivp_fma_mode_is_close_but_optional(B, oracle):
     d = np.load(GOLDEN / "ivp.npz")
     profs = (d["u"], d["v"], d["Kx"], d["Ky"], d["Kz"])
-    B.config.MARCH_MODE = "fma"
+    prev, B.config.MARCH_MODE = B.config.MARCH_MODE, "fma"
     try:
         pt, qt, P, Q = B.ivp_solver((d["a_p0"], d["a_q0"]), profs, d["z"], d["levels"], d["Lx"], d["Ly"])
     finally:
-        B.config.MARCH_MODE = "exact"
+        B.config.MARCH_MODE = prev
     assert rel_l2c(pt, d["a_ptop"]) < 1e-12
     assert rel_l2c(P, d["a_P"]) < 1e-12
 
@@ -134,15 +134,72 @@ def test_baseline_config2_full_size_against_oracle(B, oracle):
     assert 0.25 < flx.sum() <= 1.05
 
 
-def test_config2_fma_mode_within_tolerance(B, oracle):
+def _last_march_mode(B, kw):
+    from bldfm_b200 import _lib
+    geom = _lib.geometry(np.asarray(kw["srf_flx"]).shape, kw["domain"], kw["modes"], kw.get("halo"))
+    return int(_lib.lib().bldfm_plan_last_march_mode(B.get_fft_manager().plan(geom)))
+
+
+def test_config2_full_size_every_march_mode(B, oracle):
+    """BASELINE config 2 at FULL size in all three arithmetic modes: each within 1e-10 of the oracle; "auto"
+    (the default) picks the FMA-contracted march here (kappa = 7.1 <= 8.5) and is bit-identical to "fma"."""
+    kw = _config2()
+    _, oc, of = oracle.solve(nthreads=oracle.max_threads(), **kw)
+    prev = B.config.MARCH_MODE
+    got = {}
+    try:
+        for mode in ("exact", "fma", "auto"):
+            B.config.MARCH_MODE = mode
+            _, conc, flx = B.steady_state_transport_solver(**kw)
+            got[mode] = (conc, flx, _last_march_mode(B, kw))
+            assert rel_l2(conc, oc) <= TOL_F64 and rel_l2(flx, of) <= TOL_F64, mode
+    finally:
+        B.config.MARCH_MODE = prev
+    assert got["exact"][2] == 0 and got["fma"][2] == 1 and got["auto"][2] == 1
+    assert np.array_equal(got["auto"][0], got["fma"][0]) and np.array_equal(got["auto"][1], got["fma"][1])
+    # the bit-mirrored march sits two orders of magnitude closer (1e-14 vs 1e-12)
+    assert rel_l2(got["exact"][1], of) <= 1e-13
+    assert rel_l2(got["fma"][1], of) <= 1e-11
+
+
+def test_auto_mode_falls_back_to_the_exact_march_when_ill_conditioned(B, oracle):
+    """kappa gate of BLDFM_MARCH_AUTO: on a 1000 m domain (kappa = 15.3) the FMA march
+    would deviate by ~1e-8, so auto must take the bit-mirrored march; in between (2000 m, kappa = 10.3) too."""
+    from bldfm_b200 import _lib
+    prev = B.config.MARCH_MODE
+    try:
+        for dom, kap_lo in ((1000.0, 15.0), (2000.0, 10.0)):
+            kw = _config2(256)
+            kw["domain"] = (dom, dom)
+            kw["modes"] = (256, 256)
+            kw["meas_pt"] = (dom / 2, dom / 2)
+            # same grid spacing / wavenumber range as the 512^2 case of Appendix C
+            kw["domain"] = (dom / 2, dom / 2)
+            kw["meas_pt"] = (dom / 4, dom / 4)
+            geom = _lib.geometry((256, 256), kw["domain"], kw["modes"], None)
+            prob, keep = _lib.make_problem(kw["z"], kw["profiles"], kw["meas_pt"], 0.0)
+            kap = C.c_double(0.0)
+            _lib.check(_lib.lib().bldfm_kappa(C.byref(geom), C.byref(prob), 64, C.byref(kap)))
+            assert kap.value > kap_lo > _lib.lib().bldfm_auto_kappa_limit()
+            B.config.MARCH_MODE = "auto"
+            _, ca, fa = B.steady_state_transport_solver(**kw)
+            assert _last_march_mode(B, kw) == 0
+            B.config.MARCH_MODE = "exact"
+            _, ce, fe = B.steady_state_transport_solver(**kw)
+            assert np.array_equal(ca, ce) and np.array_equal(fa, fe)
+    finally:
+        B.config.MARCH_MODE = prev
+
+
+def test_fma_mode_within_tolerance_on_a_moderately_conditioned_case(B, oracle):
     kw = _config2(256)
     kw["domain"] = (2000.0, 2000.0)
     kw["meas_pt"] = (1000.0, 1000.0)
-    B.config.MARCH_MODE = "fma"
+    prev, B.config.MARCH_MODE = B.config.MARCH_MODE, "fma"
     try:
         _, conc, flx = B.steady_state_transport_solver(**kw)
     finally:
-        B.config.MARCH_MODE = "exact"
+        B.config.MARCH_MODE = prev
     _, oc, of = oracle.solve(nthreads=oracle.max_threads(), **kw)
     assert rel_l2(conc, oc) <= TOL_F64
     assert rel_l2(flx, of) <= TOL_F64
