@@ -52,6 +52,7 @@ EXPORTS = [
     "bldfm_solve_batched_accumulate", "bldfm_kappa", "bldfm_auto_kappa_limit", "bldfm_plan_last_march_mode",
     "bldfm_device_memset", "bldfm_host_register", "bldfm_host_unregister",
     "bldfm_peer_signal", "bldfm_peer_wait", "bldfm_peer_status", "bldfm_plan_march_trace",
+    "bldfm_plan_synchronize_previous", "bldfm_set_option", "bldfm_get_option",
 ]
 
 
@@ -156,6 +157,9 @@ def lib():
         "bldfm_peer_wait": (C.c_int, [vp, vp, i32, C.c_uint64, dbl]),
         "bldfm_peer_status": (C.c_int, [vp, C.POINTER(i32)]),
         "bldfm_plan_march_trace": (C.c_int, [vp, vp, i64, C.POINTER(i64)]),
+        "bldfm_plan_synchronize_previous": (C.c_int, [vp]),
+        "bldfm_set_option": (C.c_int, [C.c_char_p, i32]),
+        "bldfm_get_option": (C.c_int, [C.c_char_p, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -163,6 +167,11 @@ def lib():
         fn.argtypes = args
     _lib = L
     return L
+
+
+def set_option(name: str, value):
+    """Override a tuning switch of the library at run time (``None``: back to the environment / default)."""
+    check(lib().bldfm_set_option(name.encode(), -2**31 if value is None else int(value)))
 
 
 def last_error() -> str:

@@ -24,6 +24,7 @@
 #include "fft_herm.cuh"
 #include "fft24.cuh"
 #include "fft48.cuh"
+#include "fft24p.cuh"
 
 using namespace bldfm;
 
@@ -693,7 +694,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         if (smem > pl->smem_optin)
             return fail(BLDFM_ERR_INVALID, "nz too large for the shared-memory coefficient table (" +
                                                std::to_string(nz_max) + " levels)");
-        static const bool want_trace = fft_env_int("BLDFM_B200_MARCH_TRACE", 0) != 0;
+        const bool want_trace = fft_env_int("BLDFM_B200_MARCH_TRACE", 0) != 0;
         if (want_trace) {
             TRY(pl->march_trace.ensure(sizeof(unsigned long long) * 4 * (size_t)grid.x * grid.y));
             a.trace = static_cast<unsigned long long*>(pl->march_trace.p);
@@ -1076,6 +1077,31 @@ int bldfm_plan_synchronize(bldfm_plan* pl)
     CUDA_TRY(cudaStreamSynchronize(pl->stream));
     CUDA_TRY(cudaStreamSynchronize(pl->copy_stream));
     pl->copy_pending[0] = pl->copy_pending[1] = false;
+    return BLDFM_OK;
+}
+
+int bldfm_set_option(const char* name, int32_t value)
+{
+    if (!name || !*name) return fail(BLDFM_ERR_INVALID, "option name is empty");
+    fft_set_option(name, (int)value);
+    return BLDFM_OK;
+}
+
+int bldfm_get_option(const char* name, int32_t dflt)
+{
+    return name ? fft_env_int(name, dflt) : dflt;
+}
+
+int bldfm_plan_synchronize_previous(bldfm_plan* pl)
+{
+    if (!pl) return fail(BLDFM_ERR_INVALID, "plan is NULL");
+    DeviceGuard guard(pl->device);
+    // host-output solves alternate between two result sets; the most recent one used set (out_set ^ 1)
+    const int prev = pl->out_set;
+    if (pl->copy_pending[prev]) {
+        CUDA_TRY(cudaEventSynchronize(pl->copy_done[prev]));
+        pl->copy_pending[prev] = false;
+    }
     return BLDFM_OK;
 }
 

@@ -16,8 +16,12 @@
 #pragma once
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
+#include <mutex>
+#include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/bldfm_b200.h"
@@ -417,10 +421,35 @@ inline size_t fft_smem_bytes(int N, int cw, bool f32)
            (f32 ? sizeof(float2) : sizeof(double2));
 }
 
+// Tuning switches.  Each is read from the environment ONCE (first use) and cached -- the launch path never
+// calls getenv() again -- and can be overridden at run time with bldfm_set_option() (tests, sweeps).
+struct OptionTable {
+    std::mutex mu;
+    std::unordered_map<std::string, int> val;
+};
+inline OptionTable& fft_options()
+{
+    static OptionTable t;
+    return t;
+}
 inline int fft_env_int(const char* name, int dflt)
 {
+    OptionTable& t = fft_options();
+    std::lock_guard<std::mutex> lock(t.mu);
+    auto it = t.val.find(name);
+    if (it != t.val.end()) return it->second;
     const char* v = std::getenv(name);
-    return (v && *v) ? std::atoi(v) : dflt;
+    const int r = (v && *v) ? std::atoi(v) : dflt;
+    t.val.emplace(name, r);
+    return r;
+}
+// value = INT_MIN forgets the cached value (the environment / default is consulted again)
+inline void fft_set_option(const char* name, int value)
+{
+    OptionTable& t = fft_options();
+    std::lock_guard<std::mutex> lock(t.mu);
+    if (value == INT_MIN) t.val.erase(name);
+    else t.val[name] = value;
 }
 
 // transforms per CTA for the two passes given the shared-memory budget

@@ -342,7 +342,7 @@ inline cudaError_t fft24_launch_pass(cudaStream_t stream, size_t smem_optin, int
 {
     const bool f32 = sizeof(T) == 4;
     // overlap this grid's launch with the tail of the kernel before it in the stream (see k_fft24)
-    static const bool pdl = fft_env_int("BLDFM_B200_PDL", 1) != 0;
+    const bool pdl = fft_env_int("BLDFM_B200_PDL", 1) != 0;
     const size_t sm = fft24_smem_bytes(lq, a.cw, f32);
     const int items = a.cw * 3 * (1 << lq);
     // pass X of the radix-16 plans (150 registers) runs best as two resident CTAs of 192 threads (measured)

@@ -275,7 +275,7 @@ template <typename T, int PASS>
 inline cudaError_t fft48_launch_pass(cudaStream_t stream, size_t smem_optin, int lq, const FftHArgs& a, dim3 grid)
 {
     const bool f32 = sizeof(T) == 4;
-    static const bool pdl = fft_env_int("BLDFM_B200_PDL", 1) != 0;
+    const bool pdl = fft_env_int("BLDFM_B200_PDL", 1) != 0;
     const size_t sm = fft48_smem_bytes(lq, a.cw, f32);
     const int items = a.cw * 3 * (1 << lq);
     const int tmax = std::min(kFft48Threads, std::max(32, fft_env_int(PASS == 1 ? "BLDFM_FFT24_THREADS_Y" : "BLDFM_FFT24_THREADS_X", kFft48Threads) / 32 * 32));

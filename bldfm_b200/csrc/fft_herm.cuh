@@ -349,12 +349,27 @@ inline int fft48_pick_cw(int lq, bool f32, size_t smem_optin, int want, int64_t 
 template <typename T, int PASS>
 inline cudaError_t fft48_launch_pass(cudaStream_t stream, size_t smem_optin, int lq, const FftHArgs& a, dim3 grid);
 
+// persistent, bulk-copy pipelined variant for launches that fill the GPU many times over (fft24p.cuh)
+struct Fft24pLayout;
+inline bool fft24p_usable(int lq, int pass, const FftHArgs& a, int nfields, bool f32, size_t smem_optin, int num_sms,
+                          Fft24pLayout* lay, int* grid);
+template <typename T, int PASS>
+inline cudaError_t fft24p_launch_pass(cudaStream_t stream, size_t smem_optin, int lq, const FftHArgs& a, int nfields,
+                                      const Fft24pLayout& lay, int grid);
+
+template <typename T, int PASS>
+inline bool herm_try_fft24p(cudaStream_t stream, size_t smem_optin, int lq, const FftHArgs& a, int nfields);
+
 // launch one pass with the specialised kernel when its geometry allows (lq >= 0), else with k_fft_h
 template <typename T, int PASS>
 inline cudaError_t herm_launch_pass(cudaStream_t stream, size_t smem_optin, int lq, FftHArgs a, unsigned nfields_y,
                                     int64_t ntrans_total)
 {
     const bool f32 = sizeof(T) == 4;
+    if (lq >= 0 && a.tw24) {
+        // many work items per resident CTA: the persistent kernel that prefetches its operands with bulk copies
+        if (herm_try_fft24p<T, PASS>(stream, smem_optin, lq, a, (int)nfields_y)) return cudaGetLastError();
+    }
     // lq >= 0 implies N = 3P with P = nlx = n_out = out_off: try the two-stage variant first
     // (measured: 5 % faster than fft24.cuh when the launch fills the GPU many times over, 2 % slower for the
     // ~500 transforms of a single solve -> used for large launches only; BLDFM_B200_FFT48 = 0 never, 2 always)

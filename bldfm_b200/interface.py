@@ -26,7 +26,7 @@ from . import _lib
 from . import distributed as _dist
 from .pbl_model import ProfileBatch, compute_wind_fields_batch, vertical_profiles, vertical_profiles_batch
 from .solver import (FieldAccumulator, make_grid, measure_batched, solve_batched, steady_state_transport_solver,
-                     synchronize)
+                     synchronize, synchronize_previous)
 from .utils import compute_wind_fields, ideal_source
 
 logger = logging.getLogger("bldfm.interface")
@@ -249,18 +249,7 @@ def solve_tasks(config, tasks: Sequence[Tuple[object, int]], surface_flux=None, 
     # enqueue every chunk without waiting: the device->host copy of chunk k overlaps the kernels of
     # chunk k+1 and the host-side work of the chunks after it.  Tasks the reference answers in float32
     # (precision="single", tower at exactly (0,0)) and float64 ones go out as separate launches.
-    inflight = []
-    for want32 in (False, True):
-        idx = [t for t in pending if bool(is32[t]) == want32]
-        for part in tb.chunks(idx, per_task):
-            dest = None
-            if out is not None and not want32 and part == list(range(part[0], part[0] + len(part))):
-                dest = (out[0][part[0]:part[0] + len(part)], out[1][part[0]:part[0] + len(part)])
-            conc, flx = solve_batched(srf, problems=tb.problems(part), wait=False, out=dest,
-                                      out_pinned=out_pinned, **tb.solver_kw)
-            inflight.append((part, conc, flx, dest is not None))
-    synchronize()
-    for part, conc, flx, direct in inflight:
+    def finish(part, conc, flx, direct):
         for b, t in enumerate(part):
             tower, mi = tb.tasks[t]
             z, profiles = tb.row(t)
@@ -272,6 +261,28 @@ def solve_tasks(config, tasks: Sequence[Tuple[object, int]], surface_flux=None, 
             if cache is not None and sol.footprint:                   # solver.py:301-302
                 cache.put(z, profiles, domain, dom.modes, (tower.x, tower.y), dom.halo, sol.precision, *res)
             results[t] = _result(tower, tb.step(mi), *res)
+
+    # the post-processing of chunk k (result dictionaries, cache entries handed to the writer thread) runs
+    # while chunk k+1 computes; only pinned destinations are enqueue-only, so this needs no extra care for
+    # pageable ones (their launch returns with the results in place)
+    prev = None
+    for want32 in (False, True):
+        idx = [t for t in pending if bool(is32[t]) == want32]
+        for part in tb.chunks(idx, per_task):
+            dest = None
+            if out is not None and not want32 and part == list(range(part[0], part[0] + len(part))):
+                dest = (out[0][part[0]:part[0] + len(part)], out[1][part[0]:part[0] + len(part)])
+            conc, flx = solve_batched(srf, problems=tb.problems(part), wait=False, out=dest,
+                                      out_pinned=out_pinned, **tb.solver_kw)
+            if prev is not None:
+                synchronize_previous()
+                finish(*prev)
+            prev = (part, conc, flx, dest is not None)
+    synchronize()
+    if prev is not None:
+        finish(*prev)
+    if cache is not None and hasattr(cache, "flush"):
+        cache.flush()        # like the reference, every entry is on disk when the driver returns
     return results
 
 

@@ -302,6 +302,14 @@ def solve_batched(srf_flx, zs=None, profiles_list=None, domain=None, levels=None
     return conc, flx
 
 
+def synchronize_previous():
+    """After several ``wait=False`` batches: wait for the batch BEFORE the most recent one (its results are then
+    valid) while the most recent one may still be computing."""
+    mgr = get_fft_manager()
+    for h in list(mgr._plans.values()):
+        _lib.check(_lib.lib().bldfm_plan_synchronize_previous(h))
+
+
 def synchronize():
     """Wait for every enqueued solve / result copy on this process's plans (after ``wait=False``)."""
     mgr = get_fft_manager()

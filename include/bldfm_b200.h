@@ -94,6 +94,11 @@ typedef struct bldfm_timings {
 const char *bldfm_version(void);
 const char *bldfm_last_error_string(void);
 int  bldfm_device_count(int *count);
+/* Tuning switches (kernel selection, launch shapes; the BLDFM_B200_* / BLDFM_FFT* environment variables of
+ * DESIGN.md).  The environment is read once per switch and cached; bldfm_set_option overrides a switch at
+ * run time (value INT32_MIN: forget the override and the cached value), bldfm_get_option reads it. */
+int  bldfm_set_option(const char *name, int32_t value);
+int  bldfm_get_option(const char *name, int32_t dflt);
 
 /* Geometry (pure host arithmetic, usable without a GPU).  halo_is_none != 0 means halo=None.
  * Returns BLDFM_ERR_ODD_MODES for odd modes.                              src/bldfm/solver.py:85-130 */
@@ -116,6 +121,10 @@ int  bldfm_plan_destroy(bldfm_plan *plan);
 /* cudaStream_t of the plan as an opaque pointer (for event timing / stream interop by the caller) */
 void *bldfm_plan_stream(bldfm_plan *plan);
 int  bldfm_plan_synchronize(bldfm_plan *plan);
+/* after several BLDFM_ASYNC solves with host outputs: wait until the results of the solve BEFORE the most
+ * recent one have reached the host (the most recent one may still be running) -- lets a driver post-process
+ * batch k while batch k+1 computes */
+int  bldfm_plan_synchronize_previous(bldfm_plan *plan);
 /* number of this library's own kernels launched on the plan so far */
 int64_t bldfm_plan_launch_count(const bldfm_plan *plan);
 /* enable (1) / disable (0) per-stage event timing; read the last solve's numbers (synchronises) */

@@ -376,17 +376,27 @@ def test_default_halo_passes_equal_generic_passes(B, shape):
         _, c1, f1 = B.steady_state_transport_solver(**kw)
         c1, f1 = c1.copy(), f1.copy()
         # the two-stage variant (fft48.cuh, P = 256 / 512) is picked for large launches only: force it
-        os.environ["BLDFM_B200_FFT48"] = "2"
+        from bldfm_b200 import _lib
+        _lib.set_option("BLDFM_B200_FFT48", 2)
         try:
             _, c2, f2 = B.steady_state_transport_solver(**kw)
             c2, f2 = c2.copy(), f2.copy()
         finally:
-            del os.environ["BLDFM_B200_FFT48"]
-        os.environ["BLDFM_B200_FFT24"] = "0"
+            _lib.set_option("BLDFM_B200_FFT48", None)
+        # the persistent bulk-copy pipelined variant (fft24p.cuh) is picked for large launches only: force it;
+        # it performs the same operations per element as k_fft24 -> bit-identical
+        _lib.set_option("BLDFM_B200_FFT24P", 2)
+        try:
+            _, c3, f3 = B.steady_state_transport_solver(**kw)
+            c3, f3 = c3.copy(), f3.copy()
+        finally:
+            _lib.set_option("BLDFM_B200_FFT24P", None)
+        assert np.array_equal(c3, c1) and np.array_equal(f3, f1), case["footprint"]
+        _lib.set_option("BLDFM_B200_FFT24", 0)
         try:
             _, c0, f0 = B.steady_state_transport_solver(**kw)
         finally:
-            del os.environ["BLDFM_B200_FFT24"]
+            _lib.set_option("BLDFM_B200_FFT24", None)
         tol = 1e-13 if c0.dtype == np.float64 else 2e-6
         assert c1.dtype == c0.dtype
         assert rel_l2(c1, c0) <= tol, (case["footprint"], rel_l2(c1, c0))
