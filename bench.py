@@ -353,6 +353,22 @@ def main():
     e2e_s = time.perf_counter() - t0
     barrier()
 
+    # ---- the same leg with the other two ways of building the (X, Y, Z) grid arrays (solver.make_grid):
+    # "1" = np.meshgrid exactly as the reference (6 MB of host writes per call), "0" = zero-copy read-only views
+    e2e_grid = {}
+    grid_default = bldfm_b200.config.GRID_COPY
+    for gmode in ("1", "0"):
+        bldfm_b200.config.GRID_COPY = gmode
+        for _ in range(3):
+            grid, conc, flx = bldfm_b200.steady_state_transport_solver(**kw)
+        ng = max(10, args.steps // 4)
+        tg0 = time.perf_counter()
+        for _ in range(ng):
+            grid, conc, flx = bldfm_b200.steady_state_transport_solver(**kw)
+        e2e_grid[gmode] = (time.perf_counter() - tg0) / ng * 1e3
+    bldfm_b200.config.GRID_COPY = grid_default
+    barrier()
+
     # ---- batched figure (B distinct met conditions per launch), device-resident
     B = args.batch
     from bldfm_b200.pbl_model import vertical_profiles
@@ -501,6 +517,10 @@ def main():
                     "ms_per_step_p90_rank0": float(np.percentile(e2e_calls, 90)) * 1e3,
                     "ms_per_step_max_rank0": float(np.max(e2e_calls)) * 1e3,
                     "slow_calls_rank0": [(i, round(t * 1e3, 2)) for i, t in enumerate(e2e_calls) if t > 1e-3][:12],
+                    "grid_arrays": f"GRID_COPY={grid_default!r}: writable X, Y (copy-on-write mappings) and a freshly filled Z, "
+                                   "like the reference's np.meshgrid results",
+                    "ms_per_step_rank0_grid_meshgrid_like_reference": e2e_grid.get("1"),
+                    "ms_per_step_rank0_grid_readonly_views": e2e_grid.get("0"),
                     "api": "bldfm_b200.steady_state_transport_solver (numpy in/out)"},
             "gpu_launches": launches,
             "clocks": clocks.summary(),

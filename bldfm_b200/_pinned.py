@@ -9,6 +9,7 @@ memory held by live results is capped; beyond the cap plain pageable arrays are 
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import threading
 import weakref
@@ -44,7 +45,7 @@ class _Pool:
     def empty(self, shape, dtype):
         """np.empty(shape, dtype) on pinned memory when possible."""
         dtype = np.dtype(dtype)
-        count = int(np.prod(shape))
+        count = math.prod(shape)
         nbytes = max(_GRAIN, -(-count * dtype.itemsize // _GRAIN) * _GRAIN)
         with self.lock:
             if os.getpid() != self.pid:          # forked child: the parent's pins are not ours

@@ -22,9 +22,13 @@ DEVICE = int(os.environ.get("BLDFM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0
 # "exact": the march always mirrors the reference's operation order bit for bit.
 # "fma":   always FMA-contracted; differs from the reference at the reference's own round-off noise level.
 MARCH_MODE = os.environ.get("BLDFM_B200_MARCH", "auto")
-# True: grid arrays (X, Y, Z) are materialised like the reference's np.meshgrid (solver.py:296).
-# False: zero-copy read-only broadcast views with identical values and shapes.
-GRID_COPY = os.environ.get("BLDFM_B200_GRID_COPY", "0") == "1"
+# How the reference-signature solver builds its (X, Y, Z) grid arrays (solver.make_grid):
+#   "cow" (default): writable, independent arrays like the reference's np.meshgrid -- X and Y are private
+#          copy-on-write mappings of a cached constant (microseconds), Z is filled while the GPU works
+#   "1":   np.meshgrid exactly as the reference (solver.py:296): three full arrays written per call
+#   "0":   zero-copy READ-ONLY broadcast views with identical values and shapes
+# The batched drivers (run_bldfm_timeseries / _multitower / _parallel) always hand out the zero-copy views.
+GRID_COPY = os.environ.get("BLDFM_B200_GRID_COPY", "cow")
 # Force the library (cuFFT) transform path instead of the pruned in-house kernels.
 FFT_LIBRARY = os.environ.get("BLDFM_B200_FFT_LIBRARY", "0") == "1"
 # Use the full complex pruned passes instead of the real-output (Hermitian) half-work passes.

@@ -332,7 +332,12 @@ k_fft24p(const Fft24pArgs pa)
 inline bool fft24p_usable(int lq, int pass, const FftHArgs& a, int nfields, bool f32, size_t smem_optin, int num_sms,
                           Fft24pLayout* lay, int* grid)
 {
-    const int mode = fft_env_int("BLDFM_B200_FFT24P", 1);       // 0: never, 1: large launches, 2: whenever possible
+    // 0 (default): never, 1: launches with >= 4 work items per resident CTA, 2: whenever possible.
+    // Measured on B200 (profiles/r2_fft24p_throughput.jsonl): 128 fields of 1536^2 -> 512^2: 4.47 us per field,
+    // the same as k_fft24 (k_fft48: 4.20); 3072^2 -> 1024^2: 24.8 us per field against 18.3.  Taking the operand
+    // latency off the critical path buys nothing here: the passes are bound by the shared-memory / LSU path
+    // (operands staged through shared memory cross it once more) and the FP64 pipe, not by exposed latency.
+    const int mode = fft_env_int("BLDFM_B200_FFT24P", 0);
     if (mode == 0 || lq < 5 || lq > 9) return false;
     if (pass == 0 && (!a.hs || a.out_block != 0 || a.row0 != 0)) return false;
     if (pass == 1 && ((a.nx & 1) || a.nrow != a.nly / 2 + 1)) return false;

@@ -32,6 +32,13 @@ from .utils import compute_wind_fields, ideal_source
 logger = logging.getLogger("bldfm.interface")
 
 MAX_CHUNK_BYTES = 128 << 20   # host bytes of (conc, flx) per batched launch
+# the batched drivers return thousands of result dicts: their grids are the shared zero-copy read-only views
+# (values and shapes as the reference) unless the user asked for materialised grids (GRID_COPY = "1")
+
+
+def _grid_mode():
+    from . import config as _c
+    return "1" if _c.GRID_COPY in (True, "1") else "0"
 
 
 def _make_cache(config):
@@ -256,7 +263,7 @@ def solve_tasks(config, tasks: Sequence[Tuple[object, int]], surface_flux=None, 
             if out is not None and not direct:
                 out[0][t] = conc[b]
                 out[1][t] = flx[b]
-            grid = make_grid(z, tb.lv, domain, dom.nx, dom.ny)
+            grid = make_grid(z, tb.lv, domain, dom.nx, dom.ny, mode=_grid_mode())
             res = (grid, np.squeeze(conc[b]), np.squeeze(flx[b]))
             if cache is not None and sol.footprint:                   # solver.py:301-302
                 cache.put(z, profiles, domain, dom.modes, (tower.x, tower.y), dom.halo, sol.precision, *res)
@@ -379,7 +386,7 @@ def run_bldfm_parallel(config, max_workers=None, parallel_over: str = "towers", 
     lvarr = tb.lv
     for t, (tower, mi) in enumerate(tb.tasks):
         z, _ = tb.row(t)
-        grid = make_grid(z, lvarr, (dom.xmax, dom.ymax), dom.nx, dom.ny)
+        grid = make_grid(z, lvarr, (dom.xmax, dom.ymax), dom.nx, dom.ny, mode=_grid_mode())
         c, f = np.squeeze(conc_all[pos[t]]), np.squeeze(flx_all[pos[t]])
         if is32[t]:
             c, f = c.astype(np.float32), f.astype(np.float32)

@@ -96,30 +96,78 @@ def _levels_ptr(lv64):
 
 
 _XY_CACHE = {}
+_COW_LIMIT = 64 << 20        # bytes per grid array up to which the copy-on-write mapping is used
 
 
-def make_grid(z, lv, domain, nx, ny):
-    """(X, Y, Z) of solver.py:293-298.  Values/shapes as the reference; see config.GRID_COPY."""
+class _CowArray:
+    """A constant array kept in an anonymous memory file; ``view()`` maps it PRIVATELY: a fresh, writable,
+    independent numpy array for the price of one mmap call (microseconds) -- pages are shared with the file
+    until the caller actually writes to them."""
+
+    def __init__(self, arr):
+        import mmap
+        import os
+        arr = np.ascontiguousarray(arr)
+        self.shape, self.dtype, self.nbytes = arr.shape, arr.dtype, arr.nbytes
+        self.fd = os.memfd_create("bldfm_b200_grid", 0)
+        os.ftruncate(self.fd, max(self.nbytes, mmap.PAGESIZE))
+        with mmap.mmap(self.fd, max(self.nbytes, mmap.PAGESIZE)) as mm:
+            mm[:self.nbytes] = arr.tobytes()
+
+    def view(self):
+        import mmap
+        mm = mmap.mmap(self.fd, max(self.nbytes, mmap.PAGESIZE), flags=mmap.MAP_PRIVATE,
+                       prot=mmap.PROT_READ | mmap.PROT_WRITE)
+        return np.frombuffer(mm, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            import os
+            os.close(self.fd)
+        except Exception:
+            pass
+
+
+def make_grid(z, lv, domain, nx, ny, mode=None):
+    """(X, Y, Z) of solver.py:293-298: same values and shapes as the reference's ``np.meshgrid`` + squeeze.
+
+    ``config.GRID_COPY`` selects how they are produced:
+      "cow" (default)  writable and independent like the reference's arrays: X and Y are private
+                       copy-on-write mappings of a per-geometry constant, Z is filled afresh (that fill is
+                       done by the caller while the GPU works);  arrays above 64 MB fall back to "0"
+      "1"              ``np.meshgrid`` exactly as the reference (3 full arrays written per call)
+      "0"              zero-copy READ-ONLY broadcast views (batched drivers; fastest)
+    """
+    mode = config.GRID_COPY if mode is None else mode
     xmx, ymx = domain
     zl = np.asarray(z)[lv]
-    if config.GRID_COPY:
+    if mode in (True, "1"):
         x = np.linspace(0, xmx, nx, endpoint=False)
         y = np.linspace(0, ymx, ny, endpoint=False)
         Z, Y, X = np.meshgrid(zl, y, x, indexing="ij")
         return np.squeeze(X), np.squeeze(Y), np.squeeze(Z)
     nlv = len(zl)
-    key = (float(xmx), float(ymx), nx, ny, nlv)
+    cow = mode == "cow" and nlv * ny * nx * 8 <= _COW_LIMIT
+    key = (float(xmx), float(ymx), nx, ny, nlv, cow)
     xy = _XY_CACHE.get(key)
     if xy is None:
         x = np.linspace(0, xmx, nx, endpoint=False)
         y = np.linspace(0, ymx, ny, endpoint=False)
-        x.setflags(write=False)
-        y.setflags(write=False)
         shape = (nlv, ny, nx)
-        xy = (np.squeeze(np.broadcast_to(x[None, None, :], shape)),
-              np.squeeze(np.broadcast_to(y[None, :, None], shape)))
+        if cow:
+            xy = (_CowArray(np.squeeze(np.broadcast_to(x[None, None, :], shape))),
+                  _CowArray(np.squeeze(np.broadcast_to(y[None, :, None], shape))))
+        else:
+            x.setflags(write=False)
+            y.setflags(write=False)
+            xy = (np.squeeze(np.broadcast_to(x[None, None, :], shape)),
+                  np.squeeze(np.broadcast_to(y[None, :, None], shape)))
         if len(_XY_CACHE) < 64:
             _XY_CACHE[key] = xy
+    if cow:
+        Z = np.empty((nlv, ny, nx))
+        Z[...] = zl[:, None, None]
+        return xy[0].view(), xy[1].view(), np.squeeze(Z)
     Z = np.squeeze(np.broadcast_to(zl[:, None, None], (nlv, ny, nx)))
     return xy[0], xy[1], Z
 

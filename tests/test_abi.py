@@ -145,3 +145,30 @@ def test_kappa_matches_the_oracle_formula(L, oracle):
         assert lib.bldfm_kappa(C.byref(geom), C.byref(prob), lvl, C.byref(kap)) == 0
         want = oracle.kappa(z, [np.asarray(p, dtype=np.float64) for p in kw["profiles"]], g, float(z[lvl]))
         assert abs(kap.value - want) <= 1e-9 * max(1.0, abs(want)), name
+
+
+def test_make_grid_modes_match_the_reference_meshgrid():
+    """solver.make_grid: the three ways of producing (X, Y, Z) (config.GRID_COPY) give the values and shapes of
+    the reference's np.meshgrid + squeeze (src/bldfm/solver.py:293-298); the default copy-on-write arrays are
+    writable and independent between calls, the zero-copy views are read-only."""
+    from bldfm_b200.solver import make_grid
+    z = np.linspace(0.1, 20.0, 9)
+    for lv in (np.array([5]), np.array([0, 3, 8])):
+        for (nx, ny) in ((16, 12), (7, 5)):
+            x = np.linspace(0, 100.0, nx, endpoint=False)
+            y = np.linspace(0, 60.0, ny, endpoint=False)
+            Z, Y, X = np.meshgrid(z[lv], y, x, indexing="ij")
+            want = (np.squeeze(X), np.squeeze(Y), np.squeeze(Z))
+            for mode in ("cow", "1", "0"):
+                got = make_grid(z, lv, (100.0, 60.0), nx, ny, mode=mode)
+                for a, b in zip(got, want):
+                    assert a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b), mode
+            g1 = make_grid(z, lv, (100.0, 60.0), nx, ny, mode="cow")
+            g2 = make_grid(z, lv, (100.0, 60.0), nx, ny, mode="cow")
+            g1[0][...] -= 50.0                      # what a drop-in caller may do: X -= x0
+            g1[2][...] = 0.0
+            assert np.array_equal(g2[0], want[0]) and np.array_equal(g2[2], want[2])
+            assert np.array_equal(g1[0], want[0] - 50.0)
+            ro = make_grid(z, lv, (100.0, 60.0), nx, ny, mode="0")
+            with pytest.raises(ValueError):
+                ro[0][...] = 1.0
