@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import mmap as _mmap
 
 import numpy as np
 
@@ -96,6 +97,7 @@ def _levels_ptr(lv64):
 
 
 _XY_CACHE = {}
+_Z_CACHE = {}
 _COW_LIMIT = 64 << 20        # bytes per grid array up to which the copy-on-write mapping is used
 
 
@@ -115,10 +117,9 @@ class _CowArray:
             mm[:self.nbytes] = arr.tobytes()
 
     def view(self):
-        import mmap
-        mm = mmap.mmap(self.fd, max(self.nbytes, mmap.PAGESIZE), flags=mmap.MAP_PRIVATE,
-                       prot=mmap.PROT_READ | mmap.PROT_WRITE)
-        return np.frombuffer(mm, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+        mm = _mmap.mmap(self.fd, max(self.nbytes, _mmap.PAGESIZE), flags=_mmap.MAP_PRIVATE,
+                        prot=_mmap.PROT_READ | _mmap.PROT_WRITE)
+        return np.ndarray(self.shape, self.dtype, mm)
 
     def __del__(self):
         try:
@@ -165,9 +166,19 @@ def make_grid(z, lv, domain, nx, ny, mode=None):
         if len(_XY_CACHE) < 64:
             _XY_CACHE[key] = xy
     if cow:
-        Z = np.empty((nlv, ny, nx))
-        Z[...] = zl[:, None, None]
-        return xy[0].view(), xy[1].view(), np.squeeze(Z)
+        # Z is constant per level; footprints are taken at z[n] == meas_height, so the same few values recur:
+        # they get a copy-on-write constant as well, anything else is filled afresh
+        zkey = (nlv, ny, nx, zl.tobytes())
+        zc = _Z_CACHE.get(zkey)
+        if zc is None:
+            Z = np.empty((nlv, ny, nx))
+            Z[...] = zl[:, None, None]
+            Z = np.squeeze(Z)
+            if len(_Z_CACHE) >= 32:
+                _Z_CACHE.pop(next(iter(_Z_CACHE)))
+            _Z_CACHE[zkey] = _CowArray(Z)
+            return xy[0].view(), xy[1].view(), Z
+        return xy[0].view(), xy[1].view(), zc.view()
     Z = np.squeeze(np.broadcast_to(zl[:, None, None], (nlv, ny, nx)))
     return xy[0], xy[1], Z
 

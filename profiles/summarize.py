@@ -27,6 +27,9 @@ KEYS = [
     "dram__bytes_read.sum", "dram__bytes_write.sum",
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+    "l1tex__throughput.avg.pct_of_peak_sustained_active",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle",
     "smsp__pcsamp_warps_issue_stalled_long_scoreboard",

@@ -206,24 +206,27 @@ def leg_config5(torch, dist, rank, world, local, oracle_check=None, reps=5, size
 # ------------------------------------------------------------------------------------------------
 # config 4: 8 towers x T met steps, independent solves sharded over the ranks, final gather timed
 # ------------------------------------------------------------------------------------------------
-def synthetic_met(T, seed=0):
-    """Diurnal synthetic met series in the spirit of the reference's generate_synthetic_timeseries
-    (src/bldfm/synthetic.py:12-109): unstable days, stable nights, |L| floored at 50 m."""
-    rng = np.random.default_rng(seed)
-    hours = np.arange(T) * 0.5
-    day = np.sin(2 * np.pi * (hours - 6.0) / 24.0)
-    ustar = np.clip(0.45 + 0.3 * np.clip(day, 0, None) + 0.03 * rng.normal(size=T), 0.1, 0.8)
-    mol = np.where(day > 0, -1.0, 1.0) * np.maximum(50.0, 500.0 * (1.0 - 0.9 * np.abs(day)) + 20.0 * rng.normal(size=T))
-    ws = np.clip(4.5 + 2.5 * np.clip(day, 0, None) + 0.4 * rng.normal(size=T), 1.0, 8.0)
-    wd = (270.0 + 30.0 * rng.normal(size=T)) % 360.0
-    return ustar, mol, ws, wd
-
-
 def config4(T, ntow=8, n=512):
+    """BASELINE config 4: towers = generate_towers_grid(8, layout="grid", spacing_m=500, z_m=10,
+    seed=0), local x/y by the equirectangular map around the domain centre; met = generate_synthetic_timeseries(
+    1440, seed=0) with |L| floored at 50 m (the synthetic noise can drive L towards 0, which is ill-conditioned);
+    per-solve grid as config 2."""
     from bldfm_b200.schema import Config, Domain, Met, Parallel, SolverOptions, Tower
-    ustar, mol, ws, wd = synthetic_met(T)
-    towers = [Tower(f"T{i}", 10.0, 1000.0 + 500.0 * (i % 4), 1500.0 + 500.0 * (i // 4)) for i in range(ntow)]
-    met = Met(ustar=ustar.tolist(), mol=mol.tolist(), wind_speed=ws.tolist(), wind_dir=wd.tolist())
+    from bldfm_b200.synthetic import generate_synthetic_timeseries, generate_towers_grid
+    met_d = generate_synthetic_timeseries(n_timesteps=T, seed=0)
+    mol = np.array(met_d["mol"])
+    mol = np.where(np.abs(mol) < 50.0, np.where(mol < 0, -50.0, 50.0), mol)
+    tw = generate_towers_grid(n_towers=ntow, layout="grid", spacing_m=500, z_m=10.0, seed=0)
+    lat0 = float(np.mean([t["lat"] for t in tw]))
+    lon0 = float(np.mean([t["lon"] for t in tw]))
+    R = 6_371_000.0
+    towers = []
+    for t in tw:
+        x = R * np.radians(t["lon"] - lon0) * np.cos(np.radians(lat0)) + 2000.0
+        y = R * np.radians(t["lat"] - lat0) + 2000.0
+        towers.append(Tower(t["name"], t["z_m"], float(x), float(y), t["lat"], t["lon"]))
+    met = Met(ustar=met_d["ustar"], mol=mol.tolist(), wind_speed=met_d["wind_speed"], wind_dir=met_d["wind_dir"],
+              timestamps=met_d["timestamps"])
     dom = Domain(nx=n, ny=n, xmax=4000.0, ymax=4000.0, nz=64, modes=(n, n))
     return Config(dom, towers, met, SolverOptions(footprint=True, precision="double"), Parallel())
 

@@ -14,6 +14,7 @@ reference's imports; no reference file is modified or cop
                  (incl. the scenarios behind the reference's own tests/references/*.npz)
   refgold.npz    the reference's regression goldens source_area / plume_3d (conc, flx only)
   cache_keys.json  GreensFunctionCache keys of the reference for fixed inputs (byte-identity pin)
+  synthetic.npz  bldfm.synthetic generators for BASELINE config 4 (1440 met steps, 8 towers)      -> bitwise pin
 """
 
 from __future__ import annotations
@@ -181,8 +182,20 @@ def gen_refgold():
     save("refgold.npz", **out)
 
 
+def gen_synthetic():
+    """BASELINE config 4's inputs: the reference's synthetic met series and tower grid."""
+    from bldfm.synthetic import generate_synthetic_timeseries, generate_towers_grid
+
+    a = generate_synthetic_timeseries(n_timesteps=1440, seed=0)
+    save("synthetic.npz", ustar=a["ustar"], mol=a["mol"], wind_speed=a["wind_speed"], wind_dir=a["wind_dir"],
+         t_first=a["timestamps"][0], t_last=a["timestamps"][-1],
+         towers=json.dumps(generate_towers_grid(n_towers=8, layout="grid", spacing_m=500, z_m=10.0, seed=0)),
+         towers_random=json.dumps(generate_towers_grid(n_towers=5, layout="random", seed=2)))
+
+
 if __name__ == "__main__":
     os.chdir("/tmp")
+    gen_synthetic()
     gen_ivp()
     gen_profiles()
     gen_solves()

@@ -90,6 +90,21 @@ def test_profiles_bitwise():
             assert np.array_equal(np.asarray(a, dtype=np.float64).reshape(-1), d[f"{name}{i}"])
 
 
+def test_synthetic_generators_bitwise():
+    """bldfm_b200.synthetic == the reference's generators (src/bldfm/synthetic.py:12-185) on BASELINE config 4's
+    inputs: 1440 half-hourly steps with seed 0, 8 towers on a 500 m grid."""
+    from bldfm_b200.synthetic import generate_synthetic_timeseries, generate_towers_grid
+    d = np.load(GOLDEN / "synthetic.npz")
+    a = generate_synthetic_timeseries(n_timesteps=1440, seed=0)
+    for k in ("ustar", "mol", "wind_speed", "wind_dir"):
+        assert np.array_equal(np.array(a[k]), d[k]), k
+    assert a["timestamps"][0] == str(d["t_first"]) and a["timestamps"][-1] == str(d["t_last"])
+    assert generate_towers_grid(n_towers=8, layout="grid", spacing_m=500, z_m=10.0, seed=0) == json.loads(str(d["towers"]))
+    assert generate_towers_grid(n_towers=5, layout="random", seed=2) == json.loads(str(d["towers_random"]))
+    with pytest.raises(ValueError, match="Unknown layout"):
+        generate_towers_grid(layout="ring")
+
+
 def test_profile_errors():
     from bldfm_b200.pbl_model import vertical_profiles
     with pytest.raises(ValueError, match="Either z0 or ustar"):
