@@ -250,7 +250,11 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (bldfm_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     bldfm_b200.config.DEVICE = local
+    pinned_cores = None
     if world > 1:
+        # every rank on its own slice of the host cores, before any pinned buffer is allocated
+        from bldfm_b200.distributed import pin_to_local_cores
+        pinned_cores = pin_to_local_cores(local, world)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -367,6 +371,17 @@ def main():
             grid, conc, flx = bldfm_b200.steady_state_transport_solver(**kw)
         e2e_grid[gmode] = (time.perf_counter() - tg0) / ng * 1e3
     bldfm_b200.config.GRID_COPY = grid_default
+    # opt-in float32 delivery (half the D2H bytes; the result dtype differs from the reference's, hence opt-in)
+    bldfm_b200.config.DELIVER_FLOAT32 = True
+    for _ in range(3):
+        grid, conc32, flx32 = bldfm_b200.steady_state_transport_solver(**kw)
+    ng = max(10, args.steps // 4)
+    tg0 = time.perf_counter()
+    for _ in range(ng):
+        grid, conc32, flx32 = bldfm_b200.steady_state_transport_solver(**kw)
+    e2e_f32_ms = (time.perf_counter() - tg0) / ng * 1e3
+    bldfm_b200.config.DELIVER_FLOAT32 = False
+    f32_err = float(np.linalg.norm(flx32.astype(np.float64) - flx) / np.linalg.norm(flx))
     barrier()
 
     # ---- batched figure (B distinct met conditions per launch), device-resident
@@ -521,6 +536,10 @@ def main():
                                    "like the reference's np.meshgrid results",
                     "ms_per_step_rank0_grid_meshgrid_like_reference": e2e_grid.get("1"),
                     "ms_per_step_rank0_grid_readonly_views": e2e_grid.get("0"),
+                    "opt_in_float32_delivery": {"ms_per_step_rank0": e2e_f32_ms, "d2h_bytes_per_step": int(2 * 512 * 512 * 4),
+                                                "rel_l2_vs_float64_result": f32_err,
+                                                "switch": "bldfm_b200.config.DELIVER_FLOAT32 / BLDFM_B200_DELIVER_F32=1"},
+                    "host_cores_per_rank": (len(pinned_cores) if pinned_cores else len(os.sched_getaffinity(0))),
                     "api": "bldfm_b200.steady_state_transport_solver (numpy in/out)"},
             "gpu_launches": launches,
             "clocks": clocks.summary(),

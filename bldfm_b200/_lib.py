@@ -37,6 +37,7 @@ FFT_LIBRARY = 0x080
 FFT_FULL = 0x100
 MARCH_FULL = 0x200
 MARCH_AUTO = 0x400
+DELIVER_F32 = 0x800
 
 # every symbol include/bldfm_b200.h declares (tests check the library exports all of them)
 EXPORTS = [

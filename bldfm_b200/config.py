@@ -38,3 +38,7 @@ MARCH_FULL = os.environ.get("BLDFM_B200_MARCH_FULL", "0") == "1"
 # Device workspace budget over all cached plans of this process [bytes]; least-recently-used plans
 # are destroyed when a new plan would be created above it (a 1024^2 x 129-level plan holds ~9 GB).
 MAX_WORKSPACE_BYTES = int(os.environ.get("BLDFM_B200_MAX_WORKSPACE", str(64 << 30)))
+# Opt-in: deliver conc / flx as float32 even where the reference returns float64 (rounded on the device, half the
+# bytes over PCIe -- the device->host copy is the largest part of a single solve's end-to-end time).  Changes
+# the result dtype, hence off by default.
+DELIVER_FLOAT32 = os.environ.get("BLDFM_B200_DELIVER_F32", "0") == "1"

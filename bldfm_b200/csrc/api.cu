@@ -121,6 +121,7 @@ struct bldfm_plan {
     size_t t48_off_y[2] = {0, 0};
     DevBuf out_c, out_f;     // device outputs when the caller wants host results (set 0)
     DevBuf out_c2, out_f2;   // second set: D2H of one solve overlaps the compute of the next
+    DevBuf cast_c[2], cast_f[2];   // BLDFM_DELIVER_F32: float32 copies of the result sets
     int out_set = 0;
     cudaStream_t copy_stream = nullptr;       // D2H of results runs here
     cudaEvent_t compute_done = nullptr;
@@ -848,7 +849,20 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
 
     if (!out_dev) {
         // results leave on the copy stream so that the next solve's kernels can start meanwhile
-        const size_t nb = (size_t)nfields * out_per_field * relem;
+        size_t nb = (size_t)nfields * out_per_field * relem;
+        if ((flags & BLDFM_DELIVER_F32) && !out_f32) {
+            // opt-in: float32 delivery of float64 results (half the bytes over PCIe)
+            const int64_t n = nfields * out_per_field;
+            TRY(pl->cast_c[oset].ensure((size_t)n * sizeof(float)));
+            TRY(pl->cast_f[oset].ensure((size_t)n * sizeof(float)));
+            k_downcast2<<<grid_for(n, 256, pl->num_sms), 256, 0, pl->stream>>>(
+                static_cast<const double*>(d_conc), static_cast<const double*>(d_flx),
+                static_cast<float*>(pl->cast_c[oset].p), static_cast<float*>(pl->cast_f[oset].p), n);
+            CUDA_TRY(cudaGetLastError());
+            pl->launches++;
+            d_conc = pl->cast_c[oset].p; d_flx = pl->cast_f[oset].p;
+            nb = (size_t)n * sizeof(float);
+        }
         CUDA_TRY(cudaEventRecord(pl->compute_done, pl->stream));
         CUDA_TRY(cudaStreamWaitEvent(pl->copy_stream, pl->compute_done, 0));
         CUDA_TRY(cudaMemcpyAsync(out.conc, d_conc, nb, cudaMemcpyDeviceToHost, pl->copy_stream));
@@ -1051,6 +1065,7 @@ int bldfm_plan_destroy(bldfm_plan* pl)
     if (pl->copy_stream) cudaStreamSynchronize(pl->copy_stream);
     for (auto& kv : pl->fft_plans) cufftDestroy(kv.second);
     pl->out_c2.release(); pl->out_f2.release();
+    for (int k = 0; k < 2; ++k) { pl->cast_c[k].release(); pl->cast_f[k].release(); }
     if (pl->compute_done) cudaEventDestroy(pl->compute_done);
     for (auto& ev : pl->copy_done) if (ev) cudaEventDestroy(ev);
     if (pl->copy_stream) cudaStreamDestroy(pl->copy_stream);

@@ -315,7 +315,10 @@ constexpr int kMarchThreads = 128;
 // The per-level table of the march, staged once per CTA in shared memory from the per-solve parameter buffer.
 // (Measured alternative, round 2: the table carried in the kernel's parameter space and read with
 // warp-uniform LDC inside the loop -- no H2D copy, no staging, no barrier -- is 14 % (exact) to 36 % (fma)
-// SLOWER at config 2: the constant-bank loads do not keep up with 8 broadcast LDS.128 per step.)
+// SLOWER at config 2: the constant-bank loads do not keep up with 8 broadcast LDS.128 per step.
+// Also measured: software-pipelining the propagator of step i+1 next to the state update of step i (more
+// independent DFMA chains for the FMA mode, whose top stall is "wait") needs 12 more live registers than
+// the 72 that 7 CTAs per SM allow; the spills land inside the loop: 151 us instead of 61 us.)
 struct SmemCoef {
     const LevelCoef* sc;
     const int32_t* srow;

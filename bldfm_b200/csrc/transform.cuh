@@ -125,4 +125,16 @@ k_accumulate(const R* __restrict__ fields, double* __restrict__ acc, const int32
     }
 }
 
+// opt-in float32 delivery (BLDFM_DELIVER_F32): round the float64 fields to float32 on the device so that half
+// the bytes cross PCIe; two fields per launch
+__global__ void __launch_bounds__(256)
+k_downcast2(const double* __restrict__ a, const double* __restrict__ b, float* __restrict__ oa, float* __restrict__ ob,
+            int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        oa[i] = (float)a[i];
+        ob[i] = (float)b[i];
+    }
+}
+
 }  // namespace bldfm

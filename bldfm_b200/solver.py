@@ -38,6 +38,8 @@ def _flags(footprint, analytic, precision):
         f |= _lib.MARCH_AUTO
     elif config.MARCH_MODE != "exact":
         raise ValueError("bldfm_b200.config.MARCH_MODE must be 'exact', 'fma' or 'auto'")
+    if config.DELIVER_FLOAT32:
+        f |= _lib.DELIVER_F32
     if config.FFT_LIBRARY:
         f |= _lib.FFT_LIBRARY
     if config.FFT_FULL:
@@ -223,7 +225,7 @@ def steady_state_transport_solver(
     prob, keep = _lib.make_problem(z, profiles, meas_pt, srf_bg_conc)
     # dtype rule of solver.py:177-185,254-262 (the C side applies the same one: bldfm_output_is_f32)
     f32 = precision == "single" and not footprint and not (prob.xm * prob.xm + prob.ym * prob.ym > 0.0)
-    dt = np.float32 if f32 else np.float64
+    dt = np.float32 if (f32 or config.DELIVER_FLOAT32) else np.float64
     both, pinned = _pinned_pool.empty2((2, nlv, ny, nx), dt)
     conc, flx = both[0], both[1]
     src = None
@@ -339,7 +341,9 @@ def solve_batched(srf_flx, zs=None, profiles_list=None, domain=None, levels=None
             out[0][idx] = c
             out[1][idx] = f
         return out
-    dt = np.float32 if f32 else np.float64
+    if out is not None and out[0].dtype == np.float64:
+        flags &= ~_lib.DELIVER_F32        # caller-provided float64 destinations (shared result segment) win
+    dt = np.float32 if (f32 or (flags & _lib.DELIVER_F32)) else np.float64
     if out is None:
         conc, pinned_c = _pinned_pool.empty2((B, nlv, ny, nx), dt)
         flx, pinned_f = _pinned_pool.empty2((B, nlv, ny, nx), dt)

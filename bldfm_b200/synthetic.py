@@ -5,7 +5,7 @@ Value-for-value restatement of the two generators the reference ships for demos 
 random stream (``numpy.random.default_rng(seed)``, four normal draws in the order ustar, L, wind speed, wind
 direction), same formulas, so that BASELINE config 4 (8 towers x 1440 half-hourly steps) is built from the
 inputs SURVEY.md 8(d) names without the reference being importable.  Pinned bitwise by
-tests/golden/synthetic.npz (tests/test_oracle.py).
+the golden fixture tests/golden/synthetic.npz.
 """
 
 from __future__ import annotations

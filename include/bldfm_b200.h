@@ -48,6 +48,8 @@ extern "C" {
                                          solve's kernels (double-buffered device results, separate copy stream) */
 #define BLDFM_FFT_LIBRARY      0x080  /* force the cuFFT transform path instead of the pruned in-house kernels    */
 #define BLDFM_FFT_FULL         0x100  /* in-house back-transform without the real-output (Hermitian) halving      */
+#define BLDFM_DELIVER_F32      0x800  /* opt-in, host outputs only: conc/flx are delivered as float32 even where the
+                                         reference returns float64 (rounded on the device; half the PCIe bytes)  */
 #define BLDFM_MARCH_AUTO       0x400  /* FMA-contracted march where linear shooting is well conditioned (kappa at the
                                          highest output level <= bldfm_auto_kappa_limit() for every march of the
                                          call: predicted deviation from the reference <= 1e-11 rel-L2, SURVEY.md

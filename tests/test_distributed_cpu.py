@@ -122,3 +122,19 @@ def test_plan_tasks_groups_towers_by_height():
     keys, tg = plan_tasks(cfg, tasks)
     assert len(keys) == 10                      # 2 distinct heights x 5 met steps
     assert tg[0] == tg[1] != tg[2]              # towers A and B (z_m = 10) share a march
+
+
+def test_pin_to_local_cores_splits_the_allowed_cores():
+    import os
+    from bldfm_b200.distributed import pin_to_local_cores
+    before = sorted(os.sched_getaffinity(0))
+    try:
+        assert pin_to_local_cores(0, 1) is None                    # nothing to split
+        if len(before) >= 2:
+            mine = pin_to_local_cores(1, 2)
+            per = len(before) // 2
+            assert mine == before[per:2 * per] and sorted(os.sched_getaffinity(0)) == mine
+            os.sched_setaffinity(0, before)
+            assert pin_to_local_cores(0, 2) == before[:per]
+    finally:
+        os.sched_setaffinity(0, before)

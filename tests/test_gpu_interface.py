@@ -190,3 +190,25 @@ def test_measure_and_aggregate_drivers_match_host_reductions(gpu_lib, oracle):
         omean = np.mean([_oracle_result(oracle, cfg, tower, mi)[2] for mi in range(4)], axis=0)
         assert rel_l2(agg[tower.name]["flx"], omean) <= 1e-10
         assert agg[tower.name]["n"] == 4
+
+
+def test_float32_delivery_is_opt_in_and_rounds_the_float64_result(gpu_lib):
+    """config.DELIVER_FLOAT32: same solve, fields rounded to float32 on the device before the copy."""
+    import bldfm_b200
+    from bldfm_b200.pbl_model import vertical_profiles
+    z, prof = vertical_profiles(16, 10.0, (3.0, -2.0), ustar=0.4, mol=-60.0)
+    kw = dict(srf_flx=np.zeros((48, 64)), z=z, profiles=prof, domain=(960.0, 720.0), levels=[8, 16], modes=(64, 48),
+              meas_pt=(300.0, 350.0), footprint=True, precision="double")
+    _, c64, f64 = bldfm_b200.steady_state_transport_solver(**kw)
+    assert c64.dtype == np.float64
+    bldfm_b200.config.DELIVER_FLOAT32 = True
+    try:
+        _, c32, f32 = bldfm_b200.steady_state_transport_solver(**kw)
+        cb, fb = bldfm_b200.solve_batched(kw["srf_flx"], [z, z], [prof, prof], domain=kw["domain"], levels=kw["levels"],
+                                          modes=kw["modes"], meas_pts=[kw["meas_pt"]] * 2, footprint=True,
+                                          precision="double")
+    finally:
+        bldfm_b200.config.DELIVER_FLOAT32 = False
+    assert c32.dtype == np.float32 and f32.dtype == np.float32 and cb.dtype == np.float32
+    assert np.array_equal(c32, c64.astype(np.float32)) and np.array_equal(f32, f64.astype(np.float32))
+    assert np.array_equal(fb[1], f64.astype(np.float32))

@@ -105,8 +105,8 @@ def test_geometry_churn_is_bounded_by_the_plan_budget(B):
               f"peak_workspace={peak_ws / 2**20:.1f}MB device_delta={_dev_used_mb() - dev0:.0f}MB "
               f"rss_delta={_rss_mb() - rss0:.1f}MB")
         # the budget is checked before a plan is created: cached workspaces stay within budget + one plan
-        # (the largest of these geometries holds ~4 MB)
-        assert peak_ws <= budget + (8 << 20)
+        # (the largest of these geometries holds ~10 MB: padded 720 x 680, both result sets, source buffers)
+        assert peak_ws <= budget + (16 << 20)
         assert nplans < len(shapes)
         assert _dev_used_mb() - dev0 < 256.0
         assert _rss_mb() - rss0 < SINGLE_SOLVE_THRESHOLD_MB
