@@ -384,10 +384,21 @@ def run_bldfm_parallel(config, max_workers=None, parallel_over: str = "towers", 
     tb = TaskBatch(config, tasks)
     is32 = tb.is_f32()
     lvarr = tb.lv
+    gmode = _grid_mode()
+    domain = (dom.xmax, dom.ymax)
+    squeeze = nlv == 1
+    grids = {}                                  # march group -> grid tuple (towers of a group share z)
     for t, (tower, mi) in enumerate(tb.tasks):
-        z, _ = tb.row(t)
-        grid = make_grid(z, lvarr, (dom.xmax, dom.ymax), dom.nx, dom.ny, mode=_grid_mode())
-        c, f = np.squeeze(conc_all[pos[t]]), np.squeeze(flx_all[pos[t]])
+        g = int(tb.task_group[t])
+        grid = grids.get(g)
+        if grid is None:
+            z, _ = tb.row(t)
+            grid = grids[g] = make_grid(z, lvarr, domain, dom.nx, dom.ny, mode=gmode)
+        c, f = conc_all[pos[t]], flx_all[pos[t]]
+        if squeeze:
+            c, f = c[0], f[0]
+        if dom.ny == 1 or dom.nx == 1:
+            c, f = np.squeeze(c), np.squeeze(f)
         if is32[t]:
             c, f = c.astype(np.float32), f.astype(np.float32)
         out[tower.name][mi] = _result(tower, tb.step(mi), grid, c, f)

@@ -100,6 +100,7 @@ def _levels_ptr(lv64):
 
 _XY_CACHE = {}
 _Z_CACHE = {}
+_VIEW_CACHE = {}
 _COW_LIMIT = 64 << 20        # bytes per grid array up to which the copy-on-write mapping is used
 
 
@@ -144,6 +145,12 @@ def make_grid(z, lv, domain, nx, ny, mode=None):
     mode = config.GRID_COPY if mode is None else mode
     xmx, ymx = domain
     zl = np.asarray(z)[lv]
+    if mode == "0":
+        # read-only views are immutable: one tuple per (geometry, level heights) serves every task that asks
+        vkey = (float(xmx), float(ymx), nx, ny, zl.tobytes())
+        hit = _VIEW_CACHE.get(vkey)
+        if hit is not None:
+            return hit
     if mode in (True, "1"):
         x = np.linspace(0, xmx, nx, endpoint=False)
         y = np.linspace(0, ymx, ny, endpoint=False)
@@ -182,7 +189,12 @@ def make_grid(z, lv, domain, nx, ny, mode=None):
             return xy[0].view(), xy[1].view(), Z
         return xy[0].view(), xy[1].view(), zc.view()
     Z = np.squeeze(np.broadcast_to(zl[:, None, None], (nlv, ny, nx)))
-    return xy[0], xy[1], Z
+    out = (xy[0], xy[1], Z)
+    if mode == "0":
+        if len(_VIEW_CACHE) >= 4096:
+            _VIEW_CACHE.clear()
+        _VIEW_CACHE[vkey] = out
+    return out
 
 
 def steady_state_transport_solver(

@@ -203,6 +203,43 @@ def leg_config5(torch, dist, rank, world, local, oracle_check=None, reps=5, size
     return out
 
 
+def host_link_probe(torch, dist, rank, world, local, nbytes=256 << 20):
+    """Device->host copy bandwidth into page-locked memory: rank 0 alone, then every rank at once.  The second
+    figure is the platform's ceiling for anything that delivers fields to the host from all GPUs together
+    (on this pool: ~57 GB/s for one GPU alone, ~143 GB/s for eight together; scripts/d2h_probe.py)."""
+    dev = f"cuda:{local}"
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+
+    def bw():
+        best = 0.0
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            h.copy_(d, non_blocking=True)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) * 1e-9)
+        return best
+
+    h.copy_(d)
+    _barrier(torch, dist, world)
+    alone = bw() if rank == 0 else 0.0
+    _barrier(torch, dist, world)
+    together = bw()
+    t = torch.tensor([together], dtype=torch.float64, device=dev)
+    tmin = t.clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+    a = torch.tensor([alone], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(a, op=dist.ReduceOp.MAX)
+    return {"d2h_gbs_one_gpu_alone": float(a.item()), "d2h_gbs_all_gpus_together_aggregate": float(t.item()),
+            "d2h_gbs_all_gpus_together_min_per_gpu": float(tmin.item()), "bytes_per_copy": nbytes,
+            "note": "pinned host memory, CUDA events; the aggregate is the ceiling of every delivered-to-host number"}
+
+
 # ------------------------------------------------------------------------------------------------
 # config 4: 8 towers x T met steps, independent solves sharded over the ranks, final gather timed
 # ------------------------------------------------------------------------------------------------
@@ -321,8 +358,11 @@ def leg_config4(torch, dist, rank, world, local, T=1440, reps=2, oracle_check=No
     # ---- delivered: run_bldfm_parallel, every footprint in host memory of rank 0, gather inside the timing
     interface.run_bldfm_parallel(cfg, parallel_over="both")            # warm-up: creates + page-locks the segment
     dt, full = timed(lambda: interface.run_bldfm_parallel(cfg, parallel_over="both"), reps)
+    link = host_link_probe(torch, dist, rank, world, local)
+    res["host_link"] = link
     res["delivered"] = {"s": dt, "footprints_per_s": nfoot / dt, "bytes_to_host": need,
                         "host_gbs": need / dt * 1e-9,
+                        "frac_of_host_link": need / dt * 1e-9 / max(link["d2h_gbs_all_gpus_together_aggregate"], 1e-9),
                         "api": "bldfm_b200.run_bldfm_parallel(cfg, parallel_over='both'): result dict of every (tower, "
                                "timestep) on rank 0; each rank copies device->host over its own PCIe link into a "
                                "page-locked shared-memory segment; wall clock, barrier-bracketed, max over ranks"}
