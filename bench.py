@@ -67,8 +67,13 @@ WORKLOAD = ("BASELINE config 2: single-tower footprint 512x512, n=64 (105 levels
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of k_march on this workload, from the committed
 # `ncu --set full` captures under profiles/ (key: march mode, full-plane march)
 NCU_TRAFFIC = {("exact", True): 84736, ("exact", False): 90112, ("fma", False): 80640}
-# same for the back-transform pair in its throughput regime (128 fields): profiles/r1i_fft24_batched_ncu.txt
-NCU_TRAFFIC_BT = 998365184
+# same for the back-transform pair in its throughput regime (128 fields): profiles/r2_fft24_batched_ncu.txt
+# (pass X 273.7 + 226.2 MB, pass Y 269.5 + 229.3 MB)
+NCU_TRAFFIC_BT = 998759168
+# what ncu says binds those two kernels (same capture): the LSU data pipe shared by shared memory and L1
+NCU_BT_LSU = {"pass_x_lsu_data_pipe_pct_of_peak": 72.9, "pass_y_lsu_data_pipe_pct_of_peak": 84.6,
+              "pass_x_fp64_pipe_pct": 40.6, "pass_y_fp64_pipe_pct": 29.1, "dram_pct": [20.0, 17.7],
+              "source": "profiles/r2_fft24_batched_ncu.txt (ncu --set full, k_fft24 before the round-2 load/twiddle changes)"}
 
 
 class ClockSampler:
@@ -577,6 +582,7 @@ def main():
                 "fp64_view": {"fp64_instr_per_field_estimate": 513 * 58000,
                               "floor_us_per_field": 513 * 58000 / (peak_ops.value * 1e9) * 1e6,
                               "note": "on B200 the FP64 pipe (not HBM) is the tighter floor of this kernel; see DESIGN.md 3.2"},
+                "lsu_view": NCU_BT_LSU,
             },
             "batched": {"batch": B, "ms_per_batch": batch_ms, "solves_per_s": world * B / (batch_ms * 1e-3),
                         "mode_levels_per_s": world * B / (batch_ms * 1e-3) * mode_levels},

@@ -93,13 +93,15 @@ template <> struct Fft24Plan<7> { static constexpr int n = 2, r0 = 16, r1 = 8, r
 template <> struct Fft24Plan<8> { static constexpr int n = 2, r0 = 16, r1 = 16, r2 = 1; };
 template <> struct Fft24Plan<9> { static constexpr int n = 3, r0 = 8, r1 = 8, r2 = 8; };
 
-// split a flat work index into (transform, item): pass X keeps the items of one transform on
-// consecutive lanes (contiguous global rows), pass Y the column pairs (contiguous 16/32-byte pieces)
+// split a flat work index into (transform, item) with the TRANSFORM index fastest: the 2^lcw transforms of a CTA
+// walk the same items on neighbouring lanes, so they share every twiddle load (one 16-byte value serves 2^lcw
+// lanes: half / a quarter of the data-pipe wavefronts), pass Y's column pairs form contiguous 32 .. 64-byte
+// pieces, and pass X still reads and writes whole 128-byte lines (the lanes of one row stay 16 bytes apart)
 template <int PASS>
 __device__ __forceinline__ void fft24_split(int idx, int lcw, int nitems, int& t, int& it)
 {
-    if (PASS == 1) { it = idx >> lcw; t = idx & ((1 << lcw) - 1); }      // cw = 2^lcw transforms per CTA
-    else { t = idx / nitems; it = idx - t * nitems; }
+    if (lcw >= 0) { it = idx >> lcw; t = idx & ((1 << lcw) - 1); }
+    else { t = idx / nitems; it = idx - t * nitems; }       // partial last CTA: any number of transforms
 }
 
 // one in-place DIF stage of radix R over blocks of length M inside every sequence (not the last stage)
@@ -122,10 +124,21 @@ __device__ __forceinline__ void fft24_stage(typename Vec2<T>::type* buf, const t
         for (int u = 0; u < R; ++u) { const V x = p[u * SUB]; v[u] = {x.x, x.y}; }
         bfly_pow2<T, R>(v);
         p[0] = mk2<T>(v[0].r, v[0].i);
+        // twiddles w_M^{s d}, d = 1 .. R-1: the powers of two come from the table, the others are ONE product of
+        // two of them (w^d = w^{hi(d)} * w^{d - hi(d)}, at most two roundings beyond the table's).  These
+        // passes are bound by the L1 / shared-memory data path, not by the FP64 pipe (ncu: l1tex 75-86 %,
+        // FP64 30-40 %): 4 complex multiplies replace 4 of 7 loads for R = 8, 11 replace 11 of 15 for R = 16.
+        Cplx<T> w[R];
+#pragma unroll
+        for (int d = 1; d < R; d <<= 1) { const V wv = tw[d * SUB + s]; w[d] = {wv.x, wv.y}; }
+#pragma unroll
+        for (int d = 3; d < R; ++d) {
+            const int hi = d >= 8 ? 8 : d >= 4 ? 4 : 2;
+            if (d != hi) w[d] = cmul<T>(w[hi], w[d - hi]);
+        }
 #pragma unroll
         for (int d = 1; d < R; ++d) {
-            const V wv = tw[d * SUB + s];                       // w_M^{s d}
-            const Cplx<T> y = cmul<T>(v[d], {wv.x, wv.y});
+            const Cplx<T> y = cmul<T>(v[d], w[d]);
             p[d * SUB] = mk2<T>(y.r, y.i);
         }
     }
@@ -142,8 +155,9 @@ k_fft24(const FftHArgs a)
     extern __shared__ __align__(16) unsigned char fft_smem[];
     V* buf = reinterpret_cast<V*>(fft_smem);
     const int cw = min(a.cw, a.ntrans - (int)blockIdx.x * a.cw);
-    const int lcw = 31 - __clz(a.cw);
-    const int TS = 24 * LD + (8 >> lcw);
+    const int lcw_full = 31 - __clz(a.cw);
+    const int TS = 24 * LD + (8 >> lcw_full);
+    const int lcw = cw == a.cw ? lcw_full : -1;           // a partial last CTA (pass X: nly/2+1 rows) splits by division
     const int t0 = blockIdx.x * a.cw + (PASS == 0 ? a.row0 : 0);
     const bool second = (int)blockIdx.y >= a.nfields_first;
     const size_t field = second ? blockIdx.y - a.nfields_first : blockIdx.y;
@@ -185,11 +199,10 @@ k_fft24(const FftHArgs a)
             const size_t step = (size_t)Q * a.nx;
             V x1[9], x2[9];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { x1[u] = up[u * step]; x2[u] = up[u * step + 1]; }
+            for (int u = 0; u < 4; ++u) ld_pair(up + u * step, x1[u], x2[u]);
 #pragma unroll
-            for (int u = 4; u < 8; ++u) { x1[u] = dn[(7 - u) * step]; x2[u] = dn[(7 - u) * step + 1]; }
-            x1[8] = src[(size_t)(n1 == 0 ? 4 * Q : n1) * a.nx + 2 * tg];
-            x2[8] = src[(size_t)(n1 == 0 ? 4 * Q : n1) * a.nx + 2 * tg + 1];
+            for (int u = 4; u < 8; ++u) ld_pair(dn + (7 - u) * step, x1[u], x2[u]);
+            ld_pair(src + (size_t)(n1 == 0 ? 4 * Q : n1) * a.nx + 2 * tg, x1[8], x2[8]);
 #pragma unroll
             for (int u = 0; u < 4; ++u) v[u] = {x1[u].x - x2[u].y, sgn * (x1[u].y + x2[u].x)};        // A1 + i*A2
 #pragma unroll

@@ -278,10 +278,10 @@ k_fft24p(const Fft24pArgs pa)
         __syncthreads();
 
         // ---- in-place stages over the 24 sequences (fft24.cuh)
-        fft24_stage<T, PASS, LQ, Q, PL::r0>(buf, tw + 24 * Q, cw, cw == CW ? LCW : 0, TS);
+        fft24_stage<T, PASS, LQ, Q, PL::r0>(buf, tw + 24 * Q, cw, cw == CW ? LCW : -1, TS);
         __syncthreads();
         if (PL::n == 3) {
-            fft24_stage<T, PASS, LQ, Q / PL::r0, PL::r1>(buf, tw + 25 * Q, cw, cw == CW ? LCW : 0, TS);
+            fft24_stage<T, PASS, LQ, Q / PL::r0, PL::r1>(buf, tw + 25 * Q, cw, cw == CW ? LCW : -1, TS);
             __syncthreads();
         }
 

@@ -108,8 +108,9 @@ k_fft48(const FftHArgs a)
     extern __shared__ __align__(16) unsigned char fft_smem[];
     V* buf = reinterpret_cast<V*>(fft_smem);
     const int cw = min(a.cw, a.ntrans - (int)blockIdx.x * a.cw);
-    const int lcw = 31 - __clz(a.cw);
-    const int TS = 48 * LD + (8 >> lcw);
+    const int lcw_full = 31 - __clz(a.cw);
+    const int TS = 48 * LD + (8 >> lcw_full);
+    const int lcw = cw == a.cw ? lcw_full : -1;           // a partial last CTA (pass X: nly/2+1 rows) splits by division
     const int t0 = blockIdx.x * a.cw + (PASS == 0 ? a.row0 : 0);
     const bool second = (int)blockIdx.y >= a.nfields_first;
     const size_t field = second ? blockIdx.y - a.nfields_first : blockIdx.y;
@@ -148,18 +149,21 @@ k_fft48(const FftHArgs a)
             const size_t step = (size_t)Q * a.nx;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
-                const V x1 = up[u * step], x2 = up[u * step + 1];
+                V x1, x2;
+                ld_pair(up + u * step, x1, x2);                                              // one 256-bit load
                 v[u] = {x1.x - x2.y, sgn * (x1.y + x2.x)};                                   // A1 + i*A2
             }
 #pragma unroll
             for (int u = 8; u < 16; ++u) {
-                const V x1 = dn[(15 - u) * step], x2 = dn[(15 - u) * step + 1];
+                V x1, x2;
+                ld_pair(dn + (15 - u) * step, x1, x2);
                 v[u] = {x1.x + x2.y, sgn * (x2.x - x1.y)};                                   // conj(A1) + i*conj(A2)
             }
             if (n1 == 0) {
-                const V x1 = src[2 * tg], x2 = src[2 * tg + 1];
+                V x1, x2, y1, y2;
+                ld_pair(src + 2 * tg, x1, x2);
                 v[0] = {x1.x, sgn * x2.x};                                                   // A[0] is real
-                const V y1 = src[(size_t)(8 * Q) * a.nx + 2 * tg], y2 = src[(size_t)(8 * Q) * a.nx + 2 * tg + 1];
+                ld_pair(src + (size_t)(8 * Q) * a.nx + 2 * tg, y1, y2);
                 e = {y1.x - y2.y, sgn * (y1.y + y2.x)};
             }
         } else {

@@ -97,6 +97,22 @@ __device__ __forceinline__ Cplx<T> herm_load_y(const FftHArgs& a, const typename
     return acc;
 }
 
+// Two adjacent complex elements in ONE load: pass Y packs the column pair (x, x+1) of the intermediate, i.e. every
+// thread reads 32 contiguous bytes (complex128).  As two LDG.128 each warp instruction touches every 128-byte
+// line it needs but uses only half of it -- ncu: 7.8 data-pipe wavefronts per request in pass Y against 4.4 in
+// pass X -- and the LSU data pipe is what bounds these kernels.  sm_100 has 256-bit global loads (LDG.E.256).
+// `p` must be aligned to the size of the pair.
+__device__ __forceinline__ void ld_pair(const double2* p, double2& x1, double2& x2)
+{
+    asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(x1.x), "=d"(x1.y), "=d"(x2.x), "=d"(x2.y) : "l"(p));
+}
+__device__ __forceinline__ void ld_pair(const float2* p, float2& x1, float2& x2)
+{
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    x1 = make_float2(v.x, v.y);
+    x2 = make_float2(v.z, v.w);
+}
+
 // Operand loads are split in two steps so that all the global loads of a butterfly are in flight before
 // the first one is consumed: `fetch` is branch-free (out-of-range elements read a valid
 // dummy address and are zeroed by a select), `combine` is pure arithmetic.
