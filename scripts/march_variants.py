@@ -38,7 +38,7 @@ def one():
         L.bldfm_plan_last_timings(plan, C.byref(tm))
         t.append(tm.march_ms)
         tot.append(tm.forward_ms + tm.march_ms + tm.inverse_ms)
-    out = {"mode": bldfm_b200.config.MARCH_MODE, "param": os.environ.get("BLDFM_B200_MARCH_PARAM", "1"),
+    out = {"mode": bldfm_b200.config.MARCH_MODE, "big": os.environ.get("BLDFM_B200_MARCH_BIG", "1"),
            "S": len(z) - 1, "march_us": float(np.median(t)) * 1e3, "solve_us": float(np.median(tot)) * 1e3,
            "fma_used": int(L.bldfm_plan_last_march_mode(plan))}
     if os.environ.get("BLDFM_B200_MARCH_TRACE") == "1":
@@ -61,13 +61,14 @@ if __name__ == "__main__":
     if os.environ.get("VAR_CHILD") == "1":
         one()
     else:
-        for mode in ("exact", "fma", "auto"):
-            for param in ("0", "1"):
+        # 128-thread CTAs (7 per SM) against the lock-step 896-thread CTA (one per SM), with per-CTA traces
+        for mode in ("exact", "fma"):
+            for big in ("0", "1"):
                 for trace in ("0", "1"):
-                    env = dict(os.environ, VAR_CHILD="1", BLDFM_B200_MARCH=mode, BLDFM_B200_MARCH_PARAM=param,
+                    env = dict(os.environ, VAR_CHILD="1", BLDFM_B200_MARCH=mode, BLDFM_B200_MARCH_BIG=big,
                                BLDFM_B200_MARCH_TRACE=trace)
                     subprocess.run([sys.executable, __file__], env=env, check=False)
-        for n in (16, 128):
-            for param in ("0", "1"):
-                env = dict(os.environ, VAR_CHILD="1", BLDFM_B200_MARCH="exact", BLDFM_B200_MARCH_PARAM=param, VAR_N=str(n))
+        for n in (16, 128, 256):
+            for big in ("0", "2"):
+                env = dict(os.environ, VAR_CHILD="1", BLDFM_B200_MARCH="fma", BLDFM_B200_MARCH_BIG=big, VAR_N=str(n))
                 subprocess.run([sys.executable, __file__], env=env, check=False)
