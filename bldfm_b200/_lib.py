@@ -240,12 +240,18 @@ def make_problem(z, profiles, meas_pt, srf_bg_conc):
     if len(profiles) != 5:
         raise ValueError("profiles must be (u, v, Kx, Ky, Kz)")
     n = len(z)
-    buf = np.empty((6, n), dtype=np.float64)
     try:
-        buf[0] = z
-        buf[1], buf[2], buf[3], buf[4], buf[5] = profiles
-    except ValueError:
-        raise ValueError("profiles must have the same length as z") from None
+        # fast path: six float64 vectors of one length -> one C-level concatenate
+        buf = np.concatenate((z, *profiles), dtype=np.float64, casting="unsafe")
+        if buf.shape != (6 * n,):
+            raise ValueError
+    except (ValueError, TypeError):
+        buf = np.empty((6, n), dtype=np.float64)
+        try:
+            buf[0] = z
+            buf[1], buf[2], buf[3], buf[4], buf[5] = profiles
+        except ValueError:
+            raise ValueError("profiles must have the same length as z") from None
     base = buf.ctypes.data
     row = n * 8
     p = Problem(base, base + row, base + 2 * row, base + 3 * row, base + 4 * row, base + 5 * row, n, 0,

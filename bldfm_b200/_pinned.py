@@ -29,6 +29,7 @@ class _Pool:
         self.outstanding = 0
         self.lock = threading.Lock()
         self.pid = os.getpid()
+        self._last_ptr = None
 
     def _give_back(self, nbytes, ptr, pid):
         if pid != os.getpid():
@@ -41,6 +42,15 @@ class _Pool:
         """(array, pinned): like ``empty`` but also tells whether the array really is page-locked."""
         a = self.empty(shape, dtype)
         return a, a.base is not None
+
+    def empty3(self, shape, dtype):
+        """(array, pinned, address): the address spares the caller ``array.ctypes.data`` (microseconds)."""
+        self._last_ptr = None
+        a = self.empty(shape, dtype)
+        ptr = self._last_ptr
+        if ptr is None:
+            return a, False, a.ctypes.data
+        return a, True, ptr
 
     def empty(self, shape, dtype):
         """np.empty(shape, dtype) on pinned memory when possible."""
@@ -65,7 +75,8 @@ class _Pool:
             self.outstanding += nbytes
         raw = (C.c_char * nbytes).from_address(ptr)
         weakref.finalize(raw, self._give_back, nbytes, ptr, os.getpid())
-        return np.frombuffer(raw, dtype=dtype, count=count).reshape(shape)
+        self._last_ptr = ptr
+        return np.ndarray(shape, dtype, raw)
 
     def trim(self):
         """Release every free pinned buffer back to the driver."""

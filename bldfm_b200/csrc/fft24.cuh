@@ -93,10 +93,10 @@ template <> struct Fft24Plan<7> { static constexpr int n = 2, r0 = 16, r1 = 8, r
 template <> struct Fft24Plan<8> { static constexpr int n = 2, r0 = 16, r1 = 16, r2 = 1; };
 template <> struct Fft24Plan<9> { static constexpr int n = 3, r0 = 8, r1 = 8, r2 = 8; };
 
-// split a flat work index into (transform, item) with the TRANSFORM index fastest: the 2^lcw transforms of a CTA
-// walk the same items on neighbouring lanes, so they share every twiddle load (one 16-byte value serves 2^lcw
-// lanes: half / a quarter of the data-pipe wavefronts), pass Y's column pairs form contiguous 32 .. 64-byte
-// pieces, and pass X still reads and writes whole 128-byte lines (the lanes of one row stay 16 bytes apart)
+// split a flat work index into (transform, item).  lcw >= 0: the TRANSFORM index is fastest -- the 2^lcw transforms
+// of a CTA walk the same items on neighbouring lanes (pass Y: the column pairs form contiguous 32 .. 64-byte pieces
+// and share every twiddle load); lcw < 0: the items of one transform stay on consecutive lanes (pass X: contiguous
+// global rows), any number of transforms
 template <int PASS>
 __device__ __forceinline__ void fft24_split(int idx, int lcw, int nitems, int& t, int& it)
 {
@@ -157,7 +157,9 @@ k_fft24(const FftHArgs a)
     const int cw = min(a.cw, a.ntrans - (int)blockIdx.x * a.cw);
     const int lcw_full = 31 - __clz(a.cw);
     const int TS = 24 * LD + (8 >> lcw_full);
-    const int lcw = cw == a.cw ? lcw_full : -1;           // a partial last CTA (pass X: nly/2+1 rows) splits by division
+    // pass Y always walks the column pairs first; pass X does so only on request (a.tfast): measured 3-5 % slower
+    // in the throughput regime (lanes of one row only 16 apart), a partial last CTA splits by division
+    const int lcw = (cw == a.cw && (PASS == 1 || a.tfast)) ? lcw_full : -1;
     const int t0 = blockIdx.x * a.cw + (PASS == 0 ? a.row0 : 0);
     const bool second = (int)blockIdx.y >= a.nfields_first;
     const size_t field = second ? blockIdx.y - a.nfields_first : blockIdx.y;

@@ -31,6 +31,7 @@ struct FftHArgs {
     int32_t out_off, n_out;    // output window of this pass
     int32_t nfields_first;
     int32_t hs;                // pass X: S is conjugate-symmetric (half-plane march); used by fft24.cuh
+    int32_t tfast;             // pass X: transform index fastest across lanes (BLDFM_B200_FFT_TFAST)
     // ky-slab sharding (pass X): this launch transforms the rows row0 .. row0+ntrans-1 of A and blocks
     // the kept columns by destination rank: out[field][blk][row-row0][out_block] (out_block = nx/G), or
     // straight into the peers' receive buffers out_peer[blk][field][row-row0][out_block]
@@ -428,6 +429,7 @@ inline cudaError_t herm_fft_launch(cudaStream_t stream, size_t smem_optin, const
     ax.out_off = g.px; ax.n_out = g.nx;
     ax.twiddle = tab.tw_x; ax.rev = tab.rev_x; ax.tw24 = tab.t24_x; ax.tw48 = tab.t48_x;
     ax.hs = herm_spec ? 1 : 0;
+    ax.tfast = fft_env_int("BLDFM_B200_FFT_TFAST", 0);
     const bool use24 = fft_env_int("BLDFM_B200_FFT24", 1) != 0;
     const int lqx = use24 ? fft24_lq(g.nfx, g.nlx, g.nx, g.px) : -1;
     const int lqy = use24 ? fft24_lq(g.nfy, g.nly, g.ny, g.py) : -1;

@@ -104,25 +104,32 @@ _VIEW_CACHE = {}
 _COW_LIMIT = 64 << 20        # bytes per grid array up to which the copy-on-write mapping is used
 
 
-class _CowArray:
-    """A constant array kept in an anonymous memory file; ``view()`` maps it PRIVATELY: a fresh, writable,
-    independent numpy array for the price of one mmap call (microseconds) -- pages are shared with the file
-    until the caller actually writes to them."""
+class _CowBundle:
+    """Constant arrays kept back to back in ONE anonymous memory file; ``views()`` maps the file PRIVATELY once and
+    returns fresh, writable, independent numpy arrays over it for the price of a single mmap call (microseconds) --
+    the pages are shared with the file until the caller actually writes to them."""
 
-    def __init__(self, arr):
-        import mmap
+    def __init__(self, arrays):
         import os
-        arr = np.ascontiguousarray(arr)
-        self.shape, self.dtype, self.nbytes = arr.shape, arr.dtype, arr.nbytes
+        page = _mmap.PAGESIZE
+        self.specs = []
+        off = 0
+        blobs = []
+        for a in arrays:
+            a = np.ascontiguousarray(a)
+            self.specs.append((a.shape, a.dtype, off))
+            blobs.append((off, a.tobytes()))
+            off += -(-a.nbytes // page) * page
+        self.nbytes = max(off, page)
         self.fd = os.memfd_create("bldfm_b200_grid", 0)
-        os.ftruncate(self.fd, max(self.nbytes, mmap.PAGESIZE))
-        with mmap.mmap(self.fd, max(self.nbytes, mmap.PAGESIZE)) as mm:
-            mm[:self.nbytes] = arr.tobytes()
+        os.ftruncate(self.fd, self.nbytes)
+        with _mmap.mmap(self.fd, self.nbytes) as mm:
+            for o, b in blobs:
+                mm[o:o + len(b)] = b
 
-    def view(self):
-        mm = _mmap.mmap(self.fd, max(self.nbytes, _mmap.PAGESIZE), flags=_mmap.MAP_PRIVATE,
-                        prot=_mmap.PROT_READ | _mmap.PROT_WRITE)
-        return np.ndarray(self.shape, self.dtype, mm)
+    def views(self):
+        mm = _mmap.mmap(self.fd, self.nbytes, flags=_mmap.MAP_PRIVATE, prot=_mmap.PROT_READ | _mmap.PROT_WRITE)
+        return tuple(np.ndarray(shape, dtype, mm, off) for shape, dtype, off in self.specs)
 
     def __del__(self):
         try:
@@ -158,36 +165,38 @@ def make_grid(z, lv, domain, nx, ny, mode=None):
         return np.squeeze(X), np.squeeze(Y), np.squeeze(Z)
     nlv = len(zl)
     cow = mode == "cow" and nlv * ny * nx * 8 <= _COW_LIMIT
+    if cow:
+        # footprints are taken at z[n] == meas_height, so the same level heights recur: X, Y and Z then come
+        # out of one private mapping; new heights get X, Y from their bundle and a freshly filled Z
+        zkey = (float(xmx), float(ymx), nx, ny, zl.tobytes())
+        full = _Z_CACHE.get(zkey)
+        if full is not None:
+            return full.views()
     key = (float(xmx), float(ymx), nx, ny, nlv, cow)
     xy = _XY_CACHE.get(key)
     if xy is None:
         x = np.linspace(0, xmx, nx, endpoint=False)
         y = np.linspace(0, ymx, ny, endpoint=False)
         shape = (nlv, ny, nx)
+        X = np.squeeze(np.broadcast_to(x[None, None, :], shape))
+        Y = np.squeeze(np.broadcast_to(y[None, :, None], shape))
         if cow:
-            xy = (_CowArray(np.squeeze(np.broadcast_to(x[None, None, :], shape))),
-                  _CowArray(np.squeeze(np.broadcast_to(y[None, :, None], shape))))
+            xy = _CowBundle((X, Y))
         else:
             x.setflags(write=False)
             y.setflags(write=False)
-            xy = (np.squeeze(np.broadcast_to(x[None, None, :], shape)),
-                  np.squeeze(np.broadcast_to(y[None, :, None], shape)))
+            xy = (X, Y)
         if len(_XY_CACHE) < 64:
             _XY_CACHE[key] = xy
     if cow:
-        # Z is constant per level; footprints are taken at z[n] == meas_height, so the same few values recur:
-        # they get a copy-on-write constant as well, anything else is filled afresh
-        zkey = (nlv, ny, nx, zl.tobytes())
-        zc = _Z_CACHE.get(zkey)
-        if zc is None:
-            Z = np.empty((nlv, ny, nx))
-            Z[...] = zl[:, None, None]
-            Z = np.squeeze(Z)
-            if len(_Z_CACHE) >= 32:
-                _Z_CACHE.pop(next(iter(_Z_CACHE)))
-            _Z_CACHE[zkey] = _CowArray(Z)
-            return xy[0].view(), xy[1].view(), Z
-        return xy[0].view(), xy[1].view(), zc.view()
+        Z = np.empty((nlv, ny, nx))
+        Z[...] = zl[:, None, None]
+        Z = np.squeeze(Z)
+        X, Y = xy.views()
+        if len(_Z_CACHE) >= 32:
+            _Z_CACHE.pop(next(iter(_Z_CACHE)))
+        _Z_CACHE[zkey] = _CowBundle((X, Y, Z))
+        return X, Y, Z
     Z = np.squeeze(np.broadcast_to(zl[:, None, None], (nlv, ny, nx)))
     out = (xy[0], xy[1], Z)
     if mode == "0":
@@ -238,7 +247,7 @@ def steady_state_transport_solver(
     # dtype rule of solver.py:177-185,254-262 (the C side applies the same one: bldfm_output_is_f32)
     f32 = precision == "single" and not footprint and not (prob.xm * prob.xm + prob.ym * prob.ym > 0.0)
     dt = np.float32 if (f32 or config.DELIVER_FLOAT32) else np.float64
-    both, pinned = _pinned_pool.empty2((2, nlv, ny, nx), dt)
+    both, pinned, base = _pinned_pool.empty3((2, nlv, ny, nx), dt)
     conc, flx = both[0], both[1]
     src = None
     if not footprint:
@@ -248,14 +257,16 @@ def steady_state_transport_solver(
     L = _lib.lib()
     # one address lookup for both outputs (taking an array's address from Python costs microseconds);
     # page-locked outputs: enqueue only, build the grid while the GPU works, then wait for the results
-    base = both.ctypes.data
     rc = L.bldfm_solve(
         plan, C.byref(prob), _levels_ptr(lv64), nlv,
         None if src is None else _lib.ptr(src), flags | (_lib.ASYNC if pinned else 0), base, base + conc.nbytes)
     _lib.check(rc)
     try:
         grid = make_grid(z, lv, domain, nx, ny)
-        result = (grid, np.squeeze(conc), np.squeeze(flx))
+        if nlv == 1 and ny > 1 and nx > 1:
+            result = (grid, conc[0], flx[0])                    # what np.squeeze gives, without the calls
+        else:
+            result = (grid, np.squeeze(conc), np.squeeze(flx))
     finally:
         # never leave with the copy into `both` still in flight: the buffer returns to the pool when dropped
         if pinned:
