@@ -267,6 +267,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the host link every end-to-end number rides on: D2H into pinned memory, one GPU alone and all ranks at once
+    from scripts import bench_legs as _legs
+    host_link = _legs.host_link_probe(torch, dist if world > 1 else None, rank, world, local)
+
     L = _lib.lib()
     kw = config2()
     geom = _lib.geometry(kw["srf_flx"].shape, kw["domain"], kw["modes"], None)
@@ -481,7 +485,7 @@ def main():
             configs["config3"] = bench_legs.leg_config3(torch, local)
         configs["config5"] = bench_legs.leg_config5(torch, dist_mod, rank, world, local, oracle_check=oracle_check)
         configs["config4"] = bench_legs.leg_config4(torch, dist_mod, rank, world, local, T=args.c4_steps,
-                                                    oracle_check=oracle_check)
+                                                    oracle_check=oracle_check, host_link=host_link)
         bldfm_b200.config.DEVICE = local
 
     # ---- reduce over ranks (max time)
@@ -545,6 +549,9 @@ def main():
                                                 "rel_l2_vs_float64_result": f32_err,
                                                 "switch": "bldfm_b200.config.DELIVER_FLOAT32 / BLDFM_B200_DELIVER_F32=1"},
                     "host_cores_per_rank": (len(pinned_cores) if pinned_cores else len(os.sched_getaffinity(0))),
+                    # what the platform's host link allows when every rank delivers 4.19 MB per solve at once
+                    "host_link": host_link,
+                    "host_link_bound_solves_per_s": host_link["d2h_gbs_all_gpus_together_aggregate"] * 1e9 / (2 * 512 * 512 * 8),
                     "api": "bldfm_b200.steady_state_transport_solver (numpy in/out)"},
             "gpu_launches": launches,
             "clocks": clocks.summary(),

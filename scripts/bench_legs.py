@@ -268,7 +268,7 @@ def config4(T, ntow=8, n=512):
     return Config(dom, towers, met, SolverOptions(footprint=True, precision="double"), Parallel())
 
 
-def leg_config4(torch, dist, rank, world, local, T=1440, reps=2, oracle_check=None):
+def leg_config4(torch, dist, rank, world, local, T=1440, reps=2, oracle_check=None, host_link=None):
     import bldfm_b200
     from bldfm_b200 import _lib, interface
     from bldfm_b200.utils import ideal_source
@@ -358,7 +358,7 @@ def leg_config4(torch, dist, rank, world, local, T=1440, reps=2, oracle_check=No
     # ---- delivered: run_bldfm_parallel, every footprint in host memory of rank 0, gather inside the timing
     interface.run_bldfm_parallel(cfg, parallel_over="both")            # warm-up: creates + page-locks the segment
     dt, full = timed(lambda: interface.run_bldfm_parallel(cfg, parallel_over="both"), reps)
-    link = host_link_probe(torch, dist, rank, world, local)
+    link = host_link if host_link is not None else host_link_probe(torch, dist, rank, world, local)
     res["host_link"] = link
     res["delivered"] = {"s": dt, "footprints_per_s": nfoot / dt, "bytes_to_host": need,
                         "host_gbs": need / dt * 1e-9,

@@ -138,3 +138,31 @@ def test_pin_to_local_cores_splits_the_allowed_cores():
             assert pin_to_local_cores(0, 2) == before[:per]
     finally:
         os.sched_setaffinity(0, before)
+
+
+def test_run_bldfm_parallel_without_process_group_uses_a_local_segment(monkeypatch):
+    """No torch.distributed: the same code path with one rank -- a process-local result segment, reused once the
+    previous result is dropped, never overwritten while it is alive."""
+    from bldfm_b200 import interface
+    from bldfm_b200.distributed import SharedResults
+    monkeypatch.setattr(interface, "solve_tasks", _fake_solve_tasks)
+    monkeypatch.setattr(interface, "make_grid", lambda *a, **k: (None, None, None))
+    cfg = _fake_config()
+    r1 = interface.run_bldfm_parallel(cfg, parallel_over="both")
+    r2 = interface.run_bldfm_parallel(cfg, parallel_over="time")
+    expect = _fake_solve_tasks(cfg, [(ti, mi) for ti in range(3) for mi in range(5)])
+    k = 0
+    for tower in cfg.towers:
+        for mi in range(5):
+            for r in (r1, r2):
+                assert np.array_equal(r[tower.name][mi]["conc"], expect[k]["conc"])
+                assert np.array_equal(r[tower.name][mi]["flx"], expect[k]["flx"])
+            k += 1
+    assert not np.shares_memory(r1["A"][0]["conc"], r2["A"][0]["conc"])
+    seg_ids = {id(s) for s in SharedResults._cache.values()}
+    del r1, r2, r
+    import gc
+    gc.collect()
+    r3 = interface.run_bldfm_parallel(cfg)
+    assert {id(s) for s in SharedResults._cache.values()} == seg_ids      # the freed segment was reused
+    assert np.array_equal(r3["C"][4]["flx"], expect[-1]["flx"])
