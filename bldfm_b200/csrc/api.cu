@@ -711,29 +711,8 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
                                       (int)pl->smem_optin));                                        \
         k_march<F, M><<<grid, kMarchThreads, smem, pl->stream>>>(a);                                \
     } while (0)
-            // one solve, one output level, about one wave: a single lock-step CTA per SM (march.cuh)
-            // ... or many levels: above ~250 steps the 128-byte-per-level table no longer fits seven times into
-            // an SM's shared memory and the 128-thread kernel drops to 4 CTAs (16 warps) per SM -- one big CTA
-            // keeps 28 warps on one copy of the table (BASELINE config 5: 413 steps, 52.9 KB)
-            const int64_t big_slots = (int64_t)pl->num_sms * kMarchThreadsBig;
-            const int big_mode = fft_env_int("BLDFM_B200_MARCH_BIG", 1);    // 0 never, 1 heuristics, 2 whenever possible
-            const bool one_wave = ngroups == 1 && nthreads <= big_slots && 4 * nthreads >= 3 * big_slots;
-            const bool smem_bound = 7 * (smem + 1024) > (size_t)228 * 1024 && nthreads >= big_slots;
-            const bool big = !multi && big_mode != 0 && (big_mode == 2 || one_wave || smem_bound);
-            if (big) {
-                const dim3 gbig((unsigned)((nthreads + kMarchThreadsBig - 1) / kMarchThreadsBig), (unsigned)ngroups);
-                if (want_trace) pl->march_trace_ctas = (int64_t)gbig.x * gbig.y;
-                if (fma_mode) {
-                    CUDA_TRY(cudaFuncSetAttribute(k_march<true, false, kMarchThreadsBig>,
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
-                    k_march<true, false, kMarchThreadsBig><<<gbig, kMarchThreadsBig, smem, pl->stream>>>(a);
-                } else {
-                    CUDA_TRY(cudaFuncSetAttribute(k_march<false, false, kMarchThreadsBig>,
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_optin));
-                    k_march<false, false, kMarchThreadsBig><<<gbig, kMarchThreadsBig, smem, pl->stream>>>(a);
-                }
-            } else if (fma_mode) { if (multi) LAUNCH_MARCH(true, true); else LAUNCH_MARCH(true, false); }
-            else                 { if (multi) LAUNCH_MARCH(false, true); else LAUNCH_MARCH(false, false); }
+            if (fma_mode) { if (multi) LAUNCH_MARCH(true, true); else LAUNCH_MARCH(true, false); }
+            else          { if (multi) LAUNCH_MARCH(false, true); else LAUNCH_MARCH(false, false); }
 #undef LAUNCH_MARCH
         }
         CUDA_TRY(cudaGetLastError());

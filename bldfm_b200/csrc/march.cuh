@@ -326,20 +326,13 @@ struct SmemCoef {
     __device__ __forceinline__ int row(int i, const MarchArgs&) const { return srow[i]; }
 };
 
-// LOCK > 0 (one CTA per SM, see k_march): the CTA's warps meet at a barrier every LOCK steps, so every thread --
-// also those without a mode and the (0,0) mode's -- runs the loop and the special cases are settled after it.
-template <bool FMA, bool MULTI, int LOCK, class Coef>
+template <bool FMA, bool MULTI, class Coef>
 __device__ __forceinline__ void march_body(const MarchArgs& a, const GroupDesc& gd, const TowerDesc* towers,
                                            const Coef& sc, int64_t tid)
 {
-    static_assert(LOCK == 0 || !MULTI, "the lock-step variant exists for the single-level march only");
     const int S = gd.S;
     ModeMap mm;
-    const bool valid = march_map(a, tid, mm);
-    if (!valid) {
-        if (LOCK == 0) return;
-        mm.kx = 0; mm.ky = 0; mm.mode = 0; mm.mirror = -1;          // marches a dummy, stores nothing
-    }
+    if (!march_map(a, tid, mm)) return;
     const int kx = mm.kx, ky = mm.ky;
     const double lx = a.lx[kx], ly = a.ly[ky];
 
@@ -375,7 +368,7 @@ __device__ __forceinline__ void march_body(const MarchArgs& a, const GroupDesc& 
         for (int r = visited; r < a.nlv; ++r)
             emit(r, (r == 0 && !any) ? gd.p000 : 0.0, 0.0, q0r, q0i);
     };
-    if (LOCK == 0 && is00) { mode00(); return; }
+    if (is00) { mode00(); return; }
 
     const double lx2 = lx * lx, ly2 = ly * ly;
 
@@ -395,7 +388,6 @@ __device__ __forceinline__ void march_body(const MarchArgs& a, const GroupDesc& 
             propagator<FMA>(sc[i], lx, ly, lx2, ly2, P);
             apply<FMA>(P, p1r, p1i, q1r, q1i);
             apply<FMA>(P, p2r, p2i, q2r, q2i);
-            if (LOCK > 0 && (i % LOCK) == LOCK - 1) __syncthreads();
         }
         if (snap >= 0 && snap <= S) {
             s1pr = p1r; s1pi = p1i; s1qr = q1r; s1qi = q1i;
@@ -406,11 +398,6 @@ __device__ __forceinline__ void march_body(const MarchArgs& a, const GroupDesc& 
             propagator<FMA>(sc[i], lx, ly, lx2, ly2, P);
             apply<FMA>(P, p1r, p1i, q1r, q1i);
             apply<FMA>(P, p2r, p2i, q2r, q2i);
-            if (LOCK > 0 && (i % LOCK) == LOCK - 1) __syncthreads();
-        }
-        if (LOCK > 0) {
-            if (!valid) return;
-            if (is00) { mode00(); return; }
         }
     } else {
 #pragma unroll 4
@@ -470,22 +457,17 @@ __device__ __forceinline__ void march_body(const MarchArgs& a, const GroupDesc& 
     }
 }
 
-// grid = (ceil(nthreads / THREADS), ngroups) ; dynamic smem = coef_stride*128 + nrow_of*4
+// grid = (ceil(nthreads / kMarchThreads), ngroups) ; dynamic smem = coef_stride*128 + nrow_of*4
 //
-// THREADS = 128 (default): 7 CTAs per SM, CTAs that finish make room for the next ones.
-// THREADS = 896 (kMarchThreadsBig, single-level march of ONE solve that fits in one wave): one CTA per SM whose 28
-// warps meet at a barrier every 8 steps.  Why: with 7 independent CTAs per SM the warp schedulers do not share the
-// FP64 pipe evenly -- per-CTA timestamps at config 2 show the median CTA done at 36 us (FMA) / 51 us (exact) while
-// the kernel runs until 54 / 78 us -- and in the second half too few warps are left to cover the DFMA latency.
-// In lock-step all warps finish together and the pipe stays covered until the end.
-constexpr int kMarchThreadsBig = 896;
-
-template <bool FMA, bool MULTI, int THREADS = kMarchThreads>
-__global__ void __launch_bounds__(THREADS, (THREADS == kMarchThreads ? 7 : 1))
+// (Measured alternative, round 2: ONE CTA of 896 threads per SM whose 28 warps meet at a barrier every 8 steps.
+// Motivation: per-CTA timestamps show the warp schedulers sharing the FP64 pipe unevenly between the 7 resident
+// CTAs -- the median CTA is done at 35 us (FMA) while the kernel runs until 52 us.  In lock-step every CTA takes
+// 48 us, but the kernel is no faster (60.9 vs 59.2 us FMA, 83.9 vs 82.0 us exact; 413 steps: 205 vs 199 us): the
+// uneven progress never cost throughput, and a full-SM CTA has to wait for its SM to drain completely.)
+template <bool FMA, bool MULTI>
+__global__ void __launch_bounds__(kMarchThreads, 7)
 k_march(const MarchArgs a)
 {
-    constexpr int kMarchThreads = THREADS;       // shadows the default inside this kernel
-    constexpr int LOCK = THREADS > 128 ? 8 : 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LevelCoef* sc = reinterpret_cast<LevelCoef*>(smem_raw);
     int32_t* srow = reinterpret_cast<int32_t*>(sc + a.coef_stride);
@@ -503,8 +485,8 @@ k_march(const MarchArgs a)
     }
     __syncthreads();
     if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 1] = march_now();
-    march_body<FMA, MULTI, LOCK>(a, gd, a.towers + gd.tow_begin, SmemCoef{sc, srow},
-                                 (int64_t)blockIdx.x * kMarchThreads + threadIdx.x);
+    march_body<FMA, MULTI>(a, gd, a.towers + gd.tow_begin, SmemCoef{sc, srow},
+                           (int64_t)blockIdx.x * kMarchThreads + threadIdx.x);
     if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 3] = march_now();
 }
 

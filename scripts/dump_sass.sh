@@ -3,9 +3,8 @@
 SO=bldfm_b200/libbldfm_b200.so
 cuobjdump -sass $SO > /tmp/all.sass
 ext() { awk -v pat="$1" '/Function : /{f = ($0 ~ pat)} f' /tmp/all.sass | grep -v "^\s*/\* 0x" > "$2"; }
-ext "k_marchILb0ELb0ELi128" profiles/sass_march_exact.txt
-ext "k_marchILb1ELb0ELi128" profiles/sass_march_fma.txt
-ext "k_marchILb1ELb0ELi896" profiles/sass_march_fma_lockstep896.txt
+ext "k_marchILb0ELb0" profiles/sass_march_exact.txt
+ext "k_marchILb1ELb0" profiles/sass_march_fma.txt
 ext "k_fft24IdLi0ELi6" profiles/sass_fft24_passX_c128_q64.txt
 ext "k_fft24IdLi1ELi6" profiles/sass_fft24_passY_c128_q64.txt
 ext "k_fft48IdLi0ELi5" profiles/sass_fft48_passX_c128_q32.txt

@@ -162,28 +162,6 @@ def test_config2_full_size_every_march_mode(B, oracle):
     assert rel_l2(got["fma"][1], of) <= 1e-11
 
 
-def test_lockstep_march_equals_the_default_march_bitwise(B):
-    """Config 2 fits in one wave, so its march runs as one lock-step CTA of 896 threads per SM (march.cuh);
-    the 128-thread kernel (BLDFM_B200_MARCH_BIG=0) must give the same spectra bit for bit, in both modes."""
-    from bldfm_b200 import _lib
-    from bldfm_b200.solver import spectral_fields
-    kw = _config2()
-    prev = B.config.MARCH_MODE
-    try:
-        for mode in ("exact", "fma"):
-            B.config.MARCH_MODE = mode
-            p1, q1 = spectral_fields(**kw)
-            _lib.set_option("BLDFM_B200_MARCH_BIG", 0)
-            try:
-                p0, q0 = spectral_fields(**kw)
-            finally:
-                _lib.set_option("BLDFM_B200_MARCH_BIG", None)
-            assert np.array_equal(p0, p1) and np.array_equal(q0, q1), mode
-            assert np.isfinite(p1).all() and np.isfinite(q1).all()
-    finally:
-        B.config.MARCH_MODE = prev
-
-
 def test_auto_mode_falls_back_to_the_exact_march_when_ill_conditioned(B, oracle):
     """kappa gate of BLDFM_MARCH_AUTO: on a 1000 m domain (kappa = 15.3) the FMA march
     would deviate by ~1e-8, so auto must take the bit-mirrored march; in between (2000 m, kappa = 10.3) too."""
