@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import mmap
 import os
+import threading
 import weakref
 from typing import Hashable, List, Sequence, Tuple
 
@@ -137,6 +138,7 @@ class SharedResults:
         self.nbytes = max(mmap.PAGESIZE, 2 * self.total * self.item * 8)
         self.mm = mmap.mmap(fd, self.nbytes)
         self.busy = 0
+        self._busy_lock = threading.Lock()
         self.pinned = False
         self._registered = []
         self._register()
@@ -201,12 +203,14 @@ class SharedResults:
         # every view handed out keeps `root` alive (numpy collapses view chains onto the array made from the
         # buffer), so its finaliser fires exactly when the last of them is gone
         root = np.frombuffer(self.mm, dtype=np.float64, count=2 * self.total * self.item)
-        self.busy += 1
+        with self._busy_lock:
+            self.busy += 1
         weakref.finalize(root, self._released)
         return root.reshape((2, self.total) + self.item_shape)
 
     def _released(self):
-        self.busy -= 1
+        with self._busy_lock:
+            self.busy -= 1
 
     def local_block(self):
         """(conc, flx) destination arrays ``[counts[rank], *item_shape]`` of this rank."""

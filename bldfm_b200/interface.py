@@ -228,11 +228,12 @@ class TaskBatch:
 
 
 def solve_tasks(config, tasks: Sequence[Tuple[object, int]], surface_flux=None, cache=None, out=None,
-                out_pinned=False) -> List[dict]:
+                out_pinned=False, build_results=True) -> List[dict]:
     """Solve the given (tower | tower index, met index) tasks on this process's GPU, batched.
 
     ``out=(conc, flx)``: float64 destination arrays ``[len(tasks), nlv, ny, nx]`` (e.g. this rank's block of
     a shared-memory segment) that receive the fields in task order; the result dicts then hold views.
+    ``build_results=False`` (needs ``out``) only delivers the fields and returns an empty list.
     """
     dom, sol = config.domain, config.solver
     tb = TaskBatch(config, tasks)
@@ -257,12 +258,16 @@ def solve_tasks(config, tasks: Sequence[Tuple[object, int]], surface_flux=None, 
     # chunk k+1 and the host-side work of the chunks after it.  Tasks the reference answers in float32
     # (precision="single", tower at exactly (0,0)) and float64 ones go out as separate launches.
     def finish(part, conc, flx, direct):
+        if not build_results and direct:
+            return
         for b, t in enumerate(part):
             tower, mi = tb.tasks[t]
             z, profiles = tb.row(t)
             if out is not None and not direct:
                 out[0][t] = conc[b]
                 out[1][t] = flx[b]
+            if not build_results:
+                continue
             grid = make_grid(z, tb.lv, domain, dom.nx, dom.ny, mode=_grid_mode())
             res = (grid, np.squeeze(conc[b]), np.squeeze(flx[b]))
             if cache is not None and sol.footprint:                   # solver.py:301-302
@@ -290,7 +295,7 @@ def solve_tasks(config, tasks: Sequence[Tuple[object, int]], surface_flux=None, 
         finish(*prev)
     if cache is not None and hasattr(cache, "flush"):
         cache.flush()        # like the reference, every entry is on disk when the driver returns
-    return results
+    return results if build_results else []
 
 
 def run_bldfm_timeseries(config, tower, surface_flux=None) -> list:
@@ -369,39 +374,65 @@ def run_bldfm_parallel(config, max_workers=None, parallel_over: str = "towers", 
     counts = np.bincount(owner, minlength=ws)
     seg = _dist.SharedResults.acquire((nlv, dom.ny, dom.nx), counts)
     conc_l, flx_l = seg.local_block()
-    local = solve_tasks(config, [tasks[t] for t in mine], None, None, out=(conc_l, flx_l),
-                        out_pinned=seg.pinned)
-    seg.barrier()                                  # every rank's fields have landed in the segment
+
+    # Rank 0 builds the result dictionaries (views into the segment, valid objects whatever the bytes are yet)
+    # on a helper thread WHILE the GPUs solve and copy: its main thread spends that phase blocked in CUDA waits
+    # with the GIL released, so the serial tail of the gather disappears behind the copies.
+    deferred_cast = []
+    failure = []
+
+    def build():
+        try:
+            conc_all, flx_all = seg.all_blocks()           # rank-major: rank r's tasks in its own task order
+            start = np.concatenate([[0], np.cumsum(counts)[:-1]])
+            pos = np.empty(len(tasks), dtype=np.int64)     # task -> row of the rank-major segment
+            fill = start.copy()
+            for t in range(len(tasks)):
+                pos[t] = fill[owner[t]]
+                fill[owner[t]] += 1
+            tb = TaskBatch(config, tasks)
+            is32 = tb.is_f32()
+            lvarr = tb.lv
+            gmode = _grid_mode()
+            domain = (dom.xmax, dom.ymax)
+            squeeze = nlv == 1
+            grids = {}                                     # march group -> grid tuple (towers of a group share z)
+            for t, (tower, mi) in enumerate(tb.tasks):
+                g = int(tb.task_group[t])
+                grid = grids.get(g)
+                if grid is None:
+                    z, _ = tb.row(t)
+                    grid = grids[g] = make_grid(z, lvarr, domain, dom.nx, dom.ny, mode=gmode)
+                c, f = conc_all[pos[t]], flx_all[pos[t]]
+                if squeeze:
+                    c, f = c[0], f[0]
+                if dom.ny == 1 or dom.nx == 1:
+                    c, f = np.squeeze(c), np.squeeze(f)
+                res = _result(tower, tb.step(mi), grid, c, f)
+                if is32[t]:
+                    deferred_cast.append(res)              # float32 tasks are cast once their bytes have landed
+                out[tower.name][mi] = res
+        except BaseException as e:                         # surfaced on the main thread
+            failure.append(e)
+
+    builder = None
+    if rank == 0:
+        import threading
+        builder = threading.Thread(target=build, name="bldfm-result-builder")
+        builder.start()
+    try:
+        solve_tasks(config, [tasks[t] for t in mine], None, None, out=(conc_l, flx_l), out_pinned=seg.pinned,
+                    build_results=False)
+        seg.barrier()                                  # every rank's fields have landed in the segment
+    finally:
+        if builder is not None:
+            builder.join()
     if rank != 0:
         return {}
-    conc_all, flx_all = seg.all_blocks()           # rank-major: rank r's tasks in its own task order
-    start = np.concatenate([[0], np.cumsum(counts)[:-1]])
-    pos = np.empty(len(tasks), dtype=np.int64)     # task -> row of the rank-major segment
-    fill = start.copy()
-    for t in range(len(tasks)):
-        pos[t] = fill[owner[t]]
-        fill[owner[t]] += 1
-    tb = TaskBatch(config, tasks)
-    is32 = tb.is_f32()
-    lvarr = tb.lv
-    gmode = _grid_mode()
-    domain = (dom.xmax, dom.ymax)
-    squeeze = nlv == 1
-    grids = {}                                  # march group -> grid tuple (towers of a group share z)
-    for t, (tower, mi) in enumerate(tb.tasks):
-        g = int(tb.task_group[t])
-        grid = grids.get(g)
-        if grid is None:
-            z, _ = tb.row(t)
-            grid = grids[g] = make_grid(z, lvarr, domain, dom.nx, dom.ny, mode=gmode)
-        c, f = conc_all[pos[t]], flx_all[pos[t]]
-        if squeeze:
-            c, f = c[0], f[0]
-        if dom.ny == 1 or dom.nx == 1:
-            c, f = np.squeeze(c), np.squeeze(f)
-        if is32[t]:
-            c, f = c.astype(np.float32), f.astype(np.float32)
-        out[tower.name][mi] = _result(tower, tb.step(mi), grid, c, f)
+    if failure:
+        raise failure[0]
+    for res in deferred_cast:
+        res["conc"], res["flx"] = res["conc"].astype(np.float32), res["flx"].astype(np.float32)
     return out
 
 

@@ -39,7 +39,7 @@ def _fake_config():
                   SolverOptions(footprint=True, precision="double"), Parallel())
 
 
-def _fake_solve_tasks(config, tasks, surface_flux=None, cache=None, out=None, out_pinned=False):
+def _fake_solve_tasks(config, tasks, surface_flux=None, cache=None, out=None, out_pinned=False, build_results=True):
     """Stand-in for the CUDA path: fields are a deterministic function of (tower, met index); like the real
     ``solve_tasks`` it delivers them into ``out`` (this rank's block of the shared-memory segment)."""
     from bldfm_b200 import interface
