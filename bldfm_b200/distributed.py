@@ -138,7 +138,7 @@ class SharedResults:
         self.nbytes = max(mmap.PAGESIZE, 2 * self.total * self.item * 8)
         self.mm = mmap.mmap(fd, self.nbytes)
         self.busy = 0
-        self._busy_lock = threading.Lock()
+        self._busy_lock = threading.RLock()
         self.pinned = False
         self._registered = []
         self._register()
