@@ -102,6 +102,7 @@ _XY_CACHE = {}
 _Z_CACHE = {}
 _VIEW_CACHE = {}
 _COW_LIMIT = 64 << 20        # bytes per grid array up to which the copy-on-write mapping is used
+_COW_CACHE_BYTES = 256 << 20  # memory files kept for recurring (geometry, level heights) combinations
 
 
 class _CowBundle:
@@ -193,9 +194,13 @@ def make_grid(z, lv, domain, nx, ny, mode=None):
         Z[...] = zl[:, None, None]
         Z = np.squeeze(Z)
         X, Y = xy.views()
-        if len(_Z_CACHE) >= 32:
+        # keep at most 32 bundles / 256 MB of them (oldest out first)
+        bundle = _CowBundle((X, Y, Z))
+        while _Z_CACHE and (len(_Z_CACHE) >= 32 or
+                            sum(b.nbytes for b in _Z_CACHE.values()) + bundle.nbytes > _COW_CACHE_BYTES):
             _Z_CACHE.pop(next(iter(_Z_CACHE)))
-        _Z_CACHE[zkey] = _CowBundle((X, Y, Z))
+        if bundle.nbytes <= _COW_CACHE_BYTES:
+            _Z_CACHE[zkey] = bundle
         return X, Y, Z
     Z = np.squeeze(np.broadcast_to(zl[:, None, None], (nlv, ny, nx)))
     out = (xy[0], xy[1], Z)
