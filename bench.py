@@ -64,6 +64,10 @@ WORKLOAD = ("BASELINE config 2: single-tower footprint 512x512, n=64 (105 levels
             "wind (-3,-4)), level z_m, FP64")
 
 
+# identical in both arms (the driver compares it): the workload and how the L2 is treated between timed steps
+CONFIG = {"workload": WORKLOAD,
+          "l2": "GPU arm: flushed with a 256 MiB memset between timed steps; CPU reference arm: not applicable"}
+
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of k_march on this workload, from the committed
 # `ncu --set full` captures under profiles/ (key: march mode, full-plane march)
 NCU_TRAFFIC = {("exact", True): 84736, ("exact", False): 90112, ("fma", False): 80640}
@@ -158,7 +162,7 @@ def reference_cpu_leg(steps, warmup):
     out = {"cores": cores}
     scratch = ROOT / "gpurun_out" / "_ref_scratch"          # the reference writes logs/, plots/ relative to cwd
     scratch.mkdir(parents=True, exist_ok=True)
-    for mode, extra in (("latency", ["--reps", str(max(2, min(steps, 12))), "--warmup", str(max(1, min(warmup, 2)))]),
+    for mode, extra in (("latency", ["--reps", str(max(1, steps)), "--warmup", str(max(1, warmup))]),
                         ("throughput", ["--reps", "1", "--warmup", "0", "--tasks", str(2 * cores)])):
         try:
             r = subprocess.run([sys.executable, str(runner), "--mode", mode, "--cores", str(cores), *extra],
@@ -204,8 +208,10 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     kw = config2()
-    steps = max(1, min(args.steps, 12))
-    warm = max(1, min(args.warmup, 3))
+    # a step = one warm config-2 solve of the reference (0.17-0.4 s with all host cores); K and W are honoured as
+    # given up to a two-minute budget for the latency mode (the pool mode is one extra bounded sample)
+    steps = max(1, min(args.steps, 300))
+    warm = max(1, min(args.warmup, 10))
     base, port = cpu_baseline_entries(steps, warm, kw, port_steps=max(5, min(args.steps, 40)))
     from oracle import bldfm_oracle as O
     g = O.geometry(kw["srf_flx"].shape, kw["domain"], kw["modes"], None)
@@ -215,7 +221,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 / sps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD},
+        "config": CONFIG,
         "mode_levels_per_s": sps * mode_levels,
         "cpu_baseline": base, "cpu_baseline_port": port,
         "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -529,10 +535,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "march_mode": bldfm_b200.config.MARCH_MODE,
-                       "march_arithmetic_used": "fma" if fma_mode else "exact",
-                       "fft": "cufft" if bldfm_b200.config.FFT_LIBRARY else "auto",
-                       "l2": "flushed with a 256 MiB memset between timed steps"},
+            "config": CONFIG,
+            "settings": {"march_mode": bldfm_b200.config.MARCH_MODE,
+                         "march_arithmetic_used": "fma" if fma_mode else "exact",
+                         "fft": "cufft" if bldfm_b200.config.FFT_LIBRARY else "auto",
+                         "grid_arrays": str(bldfm_b200.config.GRID_COPY)},
             "mode_levels_per_s": value * mode_levels,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(S * 128 + 80 + 24 + (S + 1) * 4),   # coef | group | tower | row_of
