@@ -288,7 +288,8 @@ def main():
         base_flags |= _lib.FFT_LIBRARY
     if bldfm_b200.config.MARCH_FULL:
         base_flags |= _lib.MARCH_FULL
-    mode_flag = {"exact": 0, "fma": _lib.MARCH_FMA, "auto": _lib.MARCH_AUTO}[bldfm_b200.config.MARCH_MODE]
+    mode_flag = {"exact": 0, "fma": _lib.MARCH_FMA, "sweep": _lib.MARCH_SWEEP,
+                 "auto": _lib.MARCH_AUTO}[bldfm_b200.config.MARCH_MODE]
     flags = base_flags | mode_flag
 
     plan = bldfm_b200.get_fft_manager().plan(geom, local)
@@ -330,7 +331,9 @@ def main():
         barrier()
     launches = int(L.bldfm_plan_launch_count(plan)) - launches0
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    fma_mode = bool(L.bldfm_plan_last_march_mode(plan))      # what "auto" picked for this workload
+    # what "auto" picked for this workload: bit-mirrored shooting, FMA-contracted shooting, or the downward sweep
+    arith = ("exact", "fma", "sweep")[int(L.bldfm_plan_last_march_mode(plan))]
+    fma_mode = arith != "exact"
 
     # ---- kernel timing for the roofline (per-stage events inside the library), both arithmetic modes
     L.bldfm_plan_set_profiling(plan, 1)
@@ -338,7 +341,7 @@ def main():
     nprof = min(args.steps, 20)
     march_by_mode = {}
     inv_ms = 0.0
-    for mname, mflag in (("exact", 0), ("fma", _lib.MARCH_FMA)):
+    for mname, mflag in (("exact", 0), ("fma", _lib.MARCH_FMA), ("sweep", _lib.MARCH_SWEEP)):
         acc = 0.0
         for _ in range(nprof):
             flush_l2()
@@ -347,8 +350,8 @@ def main():
             acc += tm.march_ms
             inv_ms += tm.inverse_ms
         march_by_mode[mname] = acc / nprof
-    inv_ms /= 2 * nprof
-    march_ms = march_by_mode["fma" if fma_mode else "exact"]
+    inv_ms /= 3 * nprof
+    march_ms = march_by_mode[arith]
     L.bldfm_plan_set_profiling(plan, 0)
 
     # ---- end-to-end leg through the public API (host in, host out)
@@ -508,17 +511,25 @@ def main():
         # (conjugate symmetry of a real source's spectra, march.cuh); the reference marches all M
         full_march = bldfm_b200.config.MARCH_FULL
         M_run = M if full_march else geom.nlx * (geom.nly // 2 + 1) + (geom.nly - 1) // 2 - 1
-        flops = 86.0 * M_run * S
+        # algorithmic flops per launch.  Shooting (exact, fma): SURVEY.md 8d's 86 per mode-step (30 for a, b, c +
+        # 2 x 28 for the two state vectors).  Sweep: 30 + 28 per mode-step (one vector), + 20 per mode-step below the
+        # output level (det(M_i) = a*a - b*c: 14, running complex product: 6) -- DESIGN.md 3.1
+        Lout = int(kw["levels"])
+        flops_by_mode = {"exact": 86.0 * M_run * S, "fma": 86.0 * M_run * S,
+                         "sweep": float(M_run) * (58.0 * S + 20.0 * Lout)}
+        flops = flops_by_mode[arith]
         achieved = flops / (march_ms * 1e-3) * 1e-12
         peak = (peak_fma.value * 2.0 if fma_mode else peak_ops.value) * 1e-3        # TFLOP/s
         alg_bytes = 2 * geom.nlx * geom.nly * 16 + S * 128
         mode_rooflines = {}
         for mname, mms in march_by_mode.items():
-            pk = (peak_fma.value * 2.0 if mname == "fma" else peak_ops.value) * 1e-3
-            mode_rooflines[mname] = {"kernel_ms": mms, "achieved": flops / (mms * 1e-3) * 1e-12, "peak": pk,
-                                     "unit": "TFLOP/s", "frac": flops / (mms * 1e-3) * 1e-12 / pk,
+            pk = (peak_fma.value * 2.0 if mname != "exact" else peak_ops.value) * 1e-3
+            fl = flops_by_mode[mname]
+            mode_rooflines[mname] = {"kernel_ms": mms, "flops_per_launch": fl,
+                                     "achieved": fl / (mms * 1e-3) * 1e-12, "peak": pk,
+                                     "unit": "TFLOP/s", "frac": fl / (mms * 1e-3) * 1e-12 / pk,
                                      "peak_source": "bldfm_fp64_peak in this run: " +
-                                                    ("DFMA x2" if mname == "fma" else "DADD/DMUL (non-fused ops)")}
+                                                    ("DFMA x2" if mname != "exact" else "DADD/DMUL (non-fused ops)")}
         # back-transform, throughput regime: algorithmic bytes per field = half-plane spectrum in, intermediate
         # written + read, real field out
         nrow = geom.nly // 2 + 1
@@ -537,7 +548,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": CONFIG,
             "settings": {"march_mode": bldfm_b200.config.MARCH_MODE,
-                         "march_arithmetic_used": "fma" if fma_mode else "exact",
+                         "march_arithmetic_used": arith,
                          "fft": "cufft" if bldfm_b200.config.FFT_LIBRARY else "auto",
                          "grid_arrays": str(bldfm_b200.config.GRID_COPY)},
             "mode_levels_per_s": value * mode_levels,
@@ -568,8 +579,8 @@ def main():
                 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
                 # capture of this kernel on this workload (profiles/r1a_march_exact_ncu.txt): the 8.4 MB
                 # of spectra it writes stay in the 126 MB L2 for the transform that follows
-                "traffic": NCU_TRAFFIC.get(("fma" if fma_mode else "exact", full_march)),
-                "arithmetic": "fma" if fma_mode else "exact", "by_mode": mode_rooflines,
+                "traffic": NCU_TRAFFIC.get((arith, full_march)),
+                "arithmetic": arith, "by_mode": mode_rooflines,
                 "flops_per_launch": flops, "kernel_ms": march_ms,
                 "modes_marched": M_run, "modes_retained": M,
                 # the same launch counted with SURVEY.md 8d's figure 86*M*S (what the reference executes)

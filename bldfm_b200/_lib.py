@@ -38,6 +38,8 @@ FFT_FULL = 0x100
 MARCH_FULL = 0x200
 MARCH_AUTO = 0x400
 DELIVER_F32 = 0x800
+OUT_MAPPED = 0x1000
+MARCH_SWEEP = 0x2000
 
 # every symbol include/bldfm_b200.h declares (tests check the library exports all of them)
 EXPORTS = [

@@ -14,13 +14,16 @@ USE_CACHE = False
 # --- bldfm_b200 additions
 # CUDA device used by this process (one process per GPU; torchrun sets LOCAL_RANK).
 DEVICE = int(os.environ.get("BLDFM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0")))
-# "auto" (default): the FMA-contracted march (46 instead of 84.5 FP64 instructions per mode-step) where linear
-#          shooting is well conditioned -- conditioning number kappa <= 8.5 at the highest output level, i.e. a
-#          predicted deviation from the reference <= 1e-11 rel-L2, a decade under the 1e-10 parity bar
-#          (calibration: profiles/r2_fma_calibration.jsonl) -- and the bit-mirrored march
-#          otherwise.
+# "auto" (default): a fast march where linear shooting is well conditioned -- conditioning number kappa <= 8.5 at
+#          the highest output level, i.e. the reference's own round-off (which is all the fast modes differ from it
+#          by) <= 1e-11 rel-L2, a decade under the 1e-10 parity bar (calibration:
+#          profiles/r2_fma_calibration.jsonl) -- and the bit-mirrored march otherwise.  The fast march is the
+#          downward sweep for one output level, the FMA-contracted upward march for several.
 # "exact": the march always mirrors the reference's operation order bit for bit.
-# "fma":   always FMA-contracted; differs from the reference at the reference's own round-off noise level.
+# "fma":   always the reference's two upward initial-value problems, FMA-contracted (46 instead of 84.5 FP64
+#          instructions per mode-step); differs from the reference at the reference's own round-off noise level.
+# "sweep": one output level: a single downward sweep from the radiation condition (30.5-42.5 instructions per
+#          mode-step, no cancellation: accurate to 1e-15 for every kappa); several levels: as "fma".
 MARCH_MODE = os.environ.get("BLDFM_B200_MARCH", "auto")
 # How the reference-signature solver builds its (X, Y, Z) grid arrays (solver.make_grid):
 #   "cow" (default): writable, independent arrays like the reference's np.meshgrid -- X and Y are private

@@ -135,7 +135,7 @@ struct bldfm_plan {
     int staging_next = 0;
     std::map<uint64_t, cufftHandle> fft_plans;
     int64_t launches = 0;
-    int last_march_fma = 0;                   // arithmetic mode the most recent march ran in (BLDFM_MARCH_AUTO)
+    int last_march_fma = 0;                   // arithmetic of the most recent march: 0 bit-mirrored, 1 FMA, 2 sweep
     bool profiling = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool ev_recorded = false;
@@ -240,6 +240,40 @@ double march_kappa(const bldfm_problem& pb, const bldfm_geometry& g, int level)
         k += std::sqrt(0.5 * (mod + re)) * (pb.z[i + 1] - pb.z[i]);          // Re sqrt(re + i*im), re >= 0
     }
     return k;
+}
+
+// May the downward sweep (march.cuh, sweep_body) run this march?  Bounds at the largest retained wavenumbers, so
+// they hold for every mode: (1) |x| = |T| h^2 / Kz <= 1.5 on every level, which keeps det(M_i) = 1 + x^2/4 -
+// x^3/36 away from zero (|det - 1| <= 0.66) -- adj(M_i) is then a true multiple of the inverse; (2) the growth of
+// the swept vector, the size of its start value and the running product of determinants stay far inside the
+// binary64 range (|log| <= 600).
+bool sweep_admissible(const bldfm_problem& pb, const bldfm_geometry& g, int level)
+{
+    const double lx = 2.0 * M_PI / (g.dx * g.nxe) * (g.nlx / 2.0);
+    const double ly = 2.0 * M_PI / (g.dy * g.nye) * (g.nly / 2.0);
+    const int S = pb.nz - 1;
+    double grow = 0.0, det_hi = 0.0, det_lo = 0.0;
+    for (int i = 0; i < S; ++i) {
+        const double kinv = 1.0 / pb.Kz[i];
+        const double h = pb.z[i + 1] - pb.z[i];
+        const double T = pb.Kx[i] * lx * lx + pb.Ky[i] * ly * ly + std::fabs(pb.u[i]) * lx + std::fabs(pb.v[i]) * ly;
+        const double y = 0.5 * kinv * T * h * h;                       // |x| / 2
+        if (!(y <= 0.75) || !(h > 0.0) || !(kinv > 0.0)) return false;
+        const double am = 1.0 + y;
+        const double bm = kinv * h * (1.0 + y / 3.0);
+        const double cm = T * h * (1.0 + y / 3.0);
+        grow += std::log(am + std::max(bm, cm));
+        if (i < level) {
+            const double e = y * y * (1.0 + 2.0 * y / 9.0);
+            det_hi += std::log1p(e);
+            det_lo += std::log1p(-e);
+        }
+    }
+    const double kt = 1.0 / pb.Kz[S];
+    const double lam = pb.Kz[S] * std::sqrt(std::hypot((pb.Kx[S] * lx * lx + pb.Ky[S] * ly * ly) * kt,
+                                                         (std::fabs(pb.u[S]) * lx + std::fabs(pb.v[S]) * ly) * kt));
+    grow += std::log(std::max(1.0, lam));
+    return grow <= 600.0 && det_hi <= 600.0 && det_lo >= -600.0 && std::isfinite(grow);
 }
 
 // kappa up to which BLDFM_MARCH_AUTO picks the FMA-contracted march.  The FMA march differs from the reference
@@ -500,15 +534,25 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     }
     const int ngroups = (int)rep.size();
     const int coef_stride = nz_max - 1;
-    // BLDFM_MARCH_AUTO: the FMA-contracted march where every march of the batch is well conditioned
-    bool fma_mode = (flags & BLDFM_MARCH_FMA) != 0;
-    if (!fma_mode && (flags & BLDFM_MARCH_AUTO) && !analytic) {
-        fma_mode = true;
+    // arithmetic of the march: 0 bit-mirrored, 1 FMA-contracted, 2 downward sweep (march.cuh).
+    // BLDFM_MARCH_AUTO: a fast mode where every march of the batch is well conditioned, i.e. where the
+    // reference's own round-off (what the fast modes differ from it by) stays below 1e-11.
+    int arith = (flags & BLDFM_MARCH_SWEEP) ? 2 : (flags & BLDFM_MARCH_FMA) ? 1 : 0;
+    if (arith == 0 && (flags & BLDFM_MARCH_AUTO) && !analytic) {
+        arith = fft_env_int("BLDFM_B200_AUTO_SWEEP", 1) ? 2 : 1;
         const int lvl = lp.last_level >= 0 ? lp.last_level : nz_max - 1;
-        for (int gi = 0; gi < ngroups && fma_mode; ++gi)
-            if (!(march_kappa(probs[rep[(size_t)gi]], g, lvl) <= auto_kappa_limit())) fma_mode = false;
+        for (int gi = 0; gi < ngroups && arith; ++gi)
+            if (!(march_kappa(probs[rep[(size_t)gi]], g, lvl) <= auto_kappa_limit())) arith = 0;
     }
-    pl->last_march_fma = fma_mode ? 1 : 0;
+    if (arith == 2) {
+        // the sweep serves one output level; it must be unable to overflow or to meet a singular step,
+        // otherwise the FMA-contracted upward march takes over
+        if (lp.visited > 1 || lp.snap_level < 0) arith = 1;
+        for (int gi = 0; gi < ngroups && arith == 2; ++gi)
+            if (!sweep_admissible(probs[rep[(size_t)gi]], g, lp.snap_level)) arith = 1;
+    }
+    const bool fma_mode = arith != 0;
+    pl->last_march_fma = arith;
 
     // ---- shifts and output dtype
     std::vector<TowerDesc> towers((size_t)nprob);
@@ -711,8 +755,9 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
                                       (int)pl->smem_optin));                                        \
         k_march<F, M><<<grid, kMarchThreads, smem, pl->stream>>>(a);                                \
     } while (0)
-            if (fma_mode) { if (multi) LAUNCH_MARCH(true, true); else LAUNCH_MARCH(true, false); }
-            else          { if (multi) LAUNCH_MARCH(false, true); else LAUNCH_MARCH(false, false); }
+            if (arith == 2 && !multi) LAUNCH_MARCH(2, false);
+            else if (fma_mode) { if (multi) LAUNCH_MARCH(1, true); else LAUNCH_MARCH(1, false); }
+            else               { if (multi) LAUNCH_MARCH(0, true); else LAUNCH_MARCH(0, false); }
 #undef LAUNCH_MARCH
         }
         CUDA_TRY(cudaGetLastError());
@@ -756,7 +801,14 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     void* d_conc = out.conc;
     void* d_flx = out.flx;
     int oset = 0;
-    if (!out_dev) {
+    // mapped page-locked outputs of a small result: the last pass stores over PCIe itself (BLDFM_OUT_MAPPED)
+    const bool cast32 = !out_dev && (flags & BLDFM_DELIVER_F32) && !out_f32;
+    bool direct = false, merged = false;
+    if (!out_dev && (flags & BLDFM_OUT_MAPPED)) {
+        const size_t each = (size_t)nfields * out_per_field * (cast32 ? sizeof(float) : relem);
+        direct = (int64_t)(2 * each) <= (int64_t)fft_env_int("BLDFM_B200_DIRECT_HOST", 0);
+    }
+    if (!out_dev && (!direct || cast32)) {
         oset = pl->out_set;
         pl->out_set ^= 1;
         DevBuf& bc = oset ? pl->out_c2 : pl->out_c;
@@ -765,13 +817,23 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         // buffers have to grow, cudaFree would race with it -> drain the copy stream first
         const size_t need = (size_t)nfields * out_per_field * relem;
         if (pl->copy_pending[oset]) {
-            if (need > bc.cap || need > bf.cap) CUDA_TRY(cudaStreamSynchronize(pl->copy_stream));
+            if (2 * need > bc.cap || need > bf.cap) CUDA_TRY(cudaStreamSynchronize(pl->copy_stream));
             else CUDA_TRY(cudaStreamWaitEvent(pl->stream, pl->copy_done[oset], 0));
             pl->copy_pending[oset] = false;
         }
-        TRY(bc.ensure(need));
-        TRY(bf.ensure(need));
-        d_conc = bc.p; d_flx = bf.p;
+        // host conc and flx adjacent (one [2][Lv][ny][nx] result block): keep the device results adjacent too
+        // so that ONE copy delivers both
+        // (only where the caller vouches that both lie in one page-locked allocation: a copy must not span two)
+        merged = !cast32 && (flags & BLDFM_OUT_MAPPED) &&
+                 static_cast<char*>(out.flx) == static_cast<char*>(out.conc) + need;
+        if (merged) {
+            TRY(bc.ensure(2 * need));
+            d_conc = bc.p; d_flx = static_cast<char*>(bc.p) + need;
+        } else {
+            TRY(bc.ensure(need));
+            TRY(bf.ensure(need));
+            d_conc = bc.p; d_flx = bf.p;
+        }
     }
     const bool forward_dir = footprint;   // fft2(norm="backward") vs ifft2(norm="forward")  solver.py:280-287
     const bool use_library = (flags & BLDFM_FFT_LIBRARY) || !pruned_fft_supported(g, spec_f32, pl->smem_optin);
@@ -850,23 +912,38 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     if (!out_dev) {
         // results leave on the copy stream so that the next solve's kernels can start meanwhile
         size_t nb = (size_t)nfields * out_per_field * relem;
-        if ((flags & BLDFM_DELIVER_F32) && !out_f32) {
+        if (cast32) {
             // opt-in: float32 delivery of float64 results (half the bytes over PCIe)
             const int64_t n = nfields * out_per_field;
-            TRY(pl->cast_c[oset].ensure((size_t)n * sizeof(float)));
-            TRY(pl->cast_f[oset].ensure((size_t)n * sizeof(float)));
+            float* dc = static_cast<float*>(out.conc);
+            float* df = static_cast<float*>(out.flx);
+            if (!direct) {
+                TRY(pl->cast_c[oset].ensure((size_t)n * sizeof(float)));
+                TRY(pl->cast_f[oset].ensure((size_t)n * sizeof(float)));
+                dc = static_cast<float*>(pl->cast_c[oset].p);
+                df = static_cast<float*>(pl->cast_f[oset].p);
+            }
             k_downcast2<<<grid_for(n, 256, pl->num_sms), 256, 0, pl->stream>>>(
-                static_cast<const double*>(d_conc), static_cast<const double*>(d_flx),
-                static_cast<float*>(pl->cast_c[oset].p), static_cast<float*>(pl->cast_f[oset].p), n);
+                static_cast<const double*>(d_conc), static_cast<const double*>(d_flx), dc, df, n);
             CUDA_TRY(cudaGetLastError());
             pl->launches++;
-            d_conc = pl->cast_c[oset].p; d_flx = pl->cast_f[oset].p;
+            d_conc = dc; d_flx = df;
             nb = (size_t)n * sizeof(float);
+        }
+        if (direct) {
+            // the kernels above wrote the host buffers; they are complete when the plan's stream is
+            if (pl->profiling) { CUDA_TRY(cudaEventRecord(pl->ev[4], pl->stream)); pl->ev_recorded = true; }
+            if (!(flags & BLDFM_ASYNC)) CUDA_TRY(cudaStreamSynchronize(pl->stream));
+            return BLDFM_OK;
         }
         CUDA_TRY(cudaEventRecord(pl->compute_done, pl->stream));
         CUDA_TRY(cudaStreamWaitEvent(pl->copy_stream, pl->compute_done, 0));
-        CUDA_TRY(cudaMemcpyAsync(out.conc, d_conc, nb, cudaMemcpyDeviceToHost, pl->copy_stream));
-        CUDA_TRY(cudaMemcpyAsync(out.flx, d_flx, nb, cudaMemcpyDeviceToHost, pl->copy_stream));
+        if (merged) {
+            CUDA_TRY(cudaMemcpyAsync(out.conc, d_conc, 2 * nb, cudaMemcpyDeviceToHost, pl->copy_stream));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(out.conc, d_conc, nb, cudaMemcpyDeviceToHost, pl->copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(out.flx, d_flx, nb, cudaMemcpyDeviceToHost, pl->copy_stream));
+        }
         CUDA_TRY(cudaEventRecord(pl->copy_done[oset], pl->copy_stream));
         pl->copy_pending[oset] = true;
         if (pl->profiling) {

@@ -13,6 +13,8 @@
 //       bit (up to the sign of exact zeros).
 //   FMA=true  (opt-in) : algebraically identical, contracted into FMAs (46 instead of 85 FP64
 //       instructions per mode-step).  Differs from the reference at the self-noise level.
+//   SWEEP (single output level): the same discrete two-point problem solved by ONE downward sweep instead of
+//       two upward initial-value problems -- see sweep_body.
 #pragma once
 
 #include "common.cuh"
@@ -312,6 +314,84 @@ __host__ __device__ __forceinline__ bool march_map(const MarchArgs& a, int64_t t
 
 constexpr int kMarchThreads = 128;
 
+// ------------------------------------------------------------------------------------------------
+// Downward sweep (arithmetic mode 2, one output level)
+//
+// The reference solves the discrete two-point problem  v_{i+1} = M_i v_i  (M_i = [[a,b],[c,a]] of solver.py:361-364),
+// q_0 = q0 at the ground, q_S = Kz*eig*p_S at the top, by linear shooting: two initial-value problems marched
+// UPWARD (solver.py:220-226) and combined with alpha (:228-235).  Upward, the wanted solution decays like
+// e^{-kappa} while both auxiliary solutions grow like e^{+kappa}: their combination cancels e^{2 kappa} of
+// round-off.  The same discrete solution follows from ONE vector swept DOWNWARD from the
+// radiation condition:  w_S = (1, Kz*eig),  w_i = adj(M_i) w_{i+1} = det(M_i) M_i^{-1} w_{i+1}  with
+// adj(M) = [[a,-b],[-c,a]] -- no division, the same a, b, c -- and
+//     v_L = w_L * q0 * prod_{i<L} det(M_i) / (w_0).q ,      det(M_i) = a*a - b*c .
+// Downward the wanted solution is the dominant one, so nothing cancels: in binary64 the sweep reproduces the
+// extended-precision discrete solution to 1e-15 for every kappa, where the reference's own binary64 shooting is
+// off by 7e-13 (kappa = 7) ... 2e-8 (kappa = 15) (tests/tools/sweep_accuracy.py).  Its deviation from the
+// reference IS the reference's round-off, hence the same kappa gate as for the FMA march.
+// Cost per mode-step: 14.5 (a, b, c) + 16 (one matrix-vector product) FP64 instructions above the output level,
+// + 12 (determinant and its running product) below it, against 46.5 for the two upward problems.
+// The host admits the sweep only where it can neither overflow nor meet a singular M_i (sweep_admissible).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void apply_adj(const Prop& P, double& pr, double& pi, double& qr, double& qi)
+{
+    const double npr = fma(P.ar, pr, fma(-P.ai, pi, fma(-P.br, qr, P.bi * qi)));
+    const double npi = fma(P.ar, pi, fma(P.ai, pr, fma(-P.br, qi, -(P.bi * qr))));
+    const double nqr = fma(P.ar, qr, fma(-P.ai, qi, fma(-P.cr, pr, P.ci * pi)));
+    const double nqi = fma(P.ar, qi, fma(P.ai, qr, fma(-P.cr, pi, -(P.ci * pr))));
+    pr = npr; pi = npi; qr = nqr; qi = nqi;
+}
+
+template <class Coef>
+__device__ __forceinline__ void sweep_body(const MarchArgs& a, const GroupDesc& gd, const Emit& emit,
+                                           const Coef& sc, double lx, double ly, double q0r, double q0i)
+{
+    const int S = gd.S;
+    const double lx2 = lx * lx, ly2 = ly * ly;
+    const int snap = a.snap_level;
+    if (snap < 0 || snap > S) {                    // the requested level is never visited: rows stay zero
+        for (int r = 0; r < a.nlv; ++r) emit(r, 0.0, 0.0, 0.0, 0.0);
+        return;
+    }
+    // radiation condition at the top (solver.py:164-174): w_S = (1, Kz_top*eig)
+    double pr = 1.0, pi = 0.0, qr, qi;
+    {
+        const double are = gd.kxk * lx2 + gd.kyk * ly2;
+        const double aim = gd.c1 * lx + gd.c2 * ly;
+        double er, ei;
+        csqrt_np(are, aim, er, ei);
+        qr = gd.kz_top * er; qi = gd.kz_top * ei;
+    }
+    Prop P;
+#pragma unroll 4
+    for (int i = S - 1; i >= snap; --i) {
+        propagator<true>(sc[i], lx, ly, lx2, ly2, P);
+        apply_adj(P, pr, pi, qr, qi);
+    }
+    const double spr = pr, spi = pi, sqr = qr, sqi = qi;      // w at the output level
+    double dr = 1.0, di = 0.0;                                // prod_{i<L} det(M_i)
+#pragma unroll 4
+    for (int i = snap - 1; i >= 0; --i) {
+        propagator<true>(sc[i], lx, ly, lx2, ly2, P);
+        apply_adj(P, pr, pi, qr, qi);
+        const double er = fma(P.ar, P.ar, fma(-P.ai, P.ai, fma(-P.br, P.cr, P.bi * P.ci)));
+        const double ei = fma(P.ar + P.ar, P.ai, -fma(P.br, P.ci, P.bi * P.cr));
+        const double ndr = fma(dr, er, -(di * ei));
+        di = fma(dr, ei, di * er);
+        dr = ndr;
+    }
+    if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 2] = march_now();
+    // s = q0 * D / (w_0).q  (Smith's division: |w_0| may be as large as e^{kappa_top})
+    double nr, ni, sr, si;
+    cmul_np(q0r, q0i, dr, di, nr, ni);
+    cdiv_np(nr, ni, qr, qi, sr, si);
+    double opr, opi, oqr, oqi;
+    cmul_np(sr, si, spr, spi, opr, opi);
+    cmul_np(sr, si, sqr, sqi, oqr, oqi);
+    if (a.nlv > 0) emit(0, opr, opi, oqr, oqi);
+    for (int r = 1; r < a.nlv; ++r) emit(r, 0.0, 0.0, 0.0, 0.0);
+}
+
 // The per-level table of the march, staged once per CTA in shared memory from the per-solve parameter buffer.
 // (Measured alternative, round 2: the table carried in the kernel's parameter space and read with
 // warp-uniform LDC inside the loop -- no H2D copy, no staging, no barrier -- is 14 % (exact) to 36 % (fma)
@@ -326,10 +406,11 @@ struct SmemCoef {
     __device__ __forceinline__ int row(int i, const MarchArgs&) const { return srow[i]; }
 };
 
-template <bool FMA, bool MULTI, class Coef>
+template <int ARITH, bool MULTI, class Coef>
 __device__ __forceinline__ void march_body(const MarchArgs& a, const GroupDesc& gd, const TowerDesc* towers,
                                            const Coef& sc, int64_t tid)
 {
+    constexpr bool FMA = ARITH != 0;
     const int S = gd.S;
     ModeMap mm;
     if (!march_map(a, tid, mm)) return;
@@ -369,6 +450,7 @@ __device__ __forceinline__ void march_body(const MarchArgs& a, const GroupDesc& 
             emit(r, (r == 0 && !any) ? gd.p000 : 0.0, 0.0, q0r, q0i);
     };
     if (is00) { mode00(); return; }
+    if (ARITH == 2 && !MULTI) { sweep_body(a, gd, emit, sc, lx, ly, q0r, q0i); return; }
 
     const double lx2 = lx * lx, ly2 = ly * ly;
 
@@ -464,7 +546,7 @@ __device__ __forceinline__ void march_body(const MarchArgs& a, const GroupDesc& 
 // CTAs -- the median CTA is done at 35 us (FMA) while the kernel runs until 52 us.  In lock-step every CTA takes
 // 48 us, but the kernel is no faster (60.9 vs 59.2 us FMA, 83.9 vs 82.0 us exact; 413 steps: 205 vs 199 us): the
 // uneven progress never cost throughput, and a full-SM CTA has to wait for its SM to drain completely.)
-template <bool FMA, bool MULTI>
+template <int ARITH, bool MULTI>
 __global__ void __launch_bounds__(kMarchThreads, 7)
 k_march(const MarchArgs a)
 {
@@ -485,7 +567,7 @@ k_march(const MarchArgs a)
     }
     __syncthreads();
     if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 1] = march_now();
-    march_body<FMA, MULTI>(a, gd, a.towers + gd.tow_begin, SmemCoef{sc, srow},
+    march_body<ARITH, MULTI>(a, gd, a.towers + gd.tow_begin, SmemCoef{sc, srow},
                            (int64_t)blockIdx.x * kMarchThreads + threadIdx.x);
     if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 3] = march_now();
 }

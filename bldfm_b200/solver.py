@@ -34,10 +34,12 @@ def _flags(footprint, analytic, precision):
         f |= _lib.ANALYTIC
     if config.MARCH_MODE == "fma":
         f |= _lib.MARCH_FMA
+    elif config.MARCH_MODE == "sweep":
+        f |= _lib.MARCH_SWEEP
     elif config.MARCH_MODE == "auto":
         f |= _lib.MARCH_AUTO
     elif config.MARCH_MODE != "exact":
-        raise ValueError("bldfm_b200.config.MARCH_MODE must be 'exact', 'fma' or 'auto'")
+        raise ValueError("bldfm_b200.config.MARCH_MODE must be 'exact', 'fma', 'sweep' or 'auto'")
     if config.DELIVER_FLOAT32:
         f |= _lib.DELIVER_F32
     if config.FFT_LIBRARY:
@@ -264,7 +266,8 @@ def steady_state_transport_solver(
     # page-locked outputs: enqueue only, build the grid while the GPU works, then wait for the results
     rc = L.bldfm_solve(
         plan, C.byref(prob), _levels_ptr(lv64), nlv,
-        None if src is None else _lib.ptr(src), flags | (_lib.ASYNC if pinned else 0), base, base + conc.nbytes)
+        None if src is None else _lib.ptr(src), flags | ((_lib.ASYNC | _lib.OUT_MAPPED) if pinned else 0), base,
+        base + conc.nbytes)
     _lib.check(rc)
     try:
         grid = make_grid(z, lv, domain, nx, ny)

@@ -50,7 +50,18 @@ extern "C" {
 #define BLDFM_FFT_FULL         0x100  /* in-house back-transform without the real-output (Hermitian) halving      */
 #define BLDFM_DELIVER_F32      0x800  /* opt-in, host outputs only: conc/flx are delivered as float32 even where the
                                          reference returns float64 (rounded on the device; half the PCIe bytes)  */
-#define BLDFM_MARCH_AUTO       0x400  /* FMA-contracted march where linear shooting is well conditioned (kappa at the
+#define BLDFM_OUT_MAPPED       0x1000 /* host outputs only: conc and flx lie in ONE page-locked allocation that is mapped
+                                         into the device address space (cudaHostAlloc / bldfm_host_alloc / one
+                                         bldfm_host_register range).  If they are adjacent, one D2H copy delivers
+                                         both.  Opt-in on top (option BLDFM_B200_DIRECT_HOST = result bytes up to
+                                         which): the last kernel stores straight into them, no D2H copy -- measured
+                                         slower for the transform's 64-byte row segments, see DESIGN.md 6         */
+#define BLDFM_MARCH_SWEEP     0x2000 /* opt-in: one output level is solved by a single downward sweep from the radiation
+                                         condition instead of two upward initial-value problems (same discrete
+                                         solution, no cancellation, fewer flops; differs from the reference by the
+                                         reference's own round-off).  Falls back to BLDFM_MARCH_FMA for several
+                                         output levels or where the sweep could overflow                        */
+#define BLDFM_MARCH_AUTO       0x400  /* fast march (sweep, else FMA-contracted) where linear shooting is well conditioned (kappa at the
                                          highest output level <= bldfm_auto_kappa_limit() for every march of the
                                          call: predicted deviation from the reference <= 1e-11 rel-L2, SURVEY.md
                                          Appendix C), the bit-mirrored march otherwise                          */
@@ -179,7 +190,8 @@ int  bldfm_solve_batched_accumulate(bldfm_plan *plan, int32_t nprob, const bldfm
 
 /* Conditioning number kappa(z[level]) of linear shooting for one problem (pure host arithmetic, usable without
  * a GPU): what BLDFM_MARCH_AUTO compares with bldfm_auto_kappa_limit() (default 8.5, env BLDFM_B200_AUTO_KAPPA).
- * bldfm_plan_last_march_mode: 1 if the plan's most recent march ran FMA-contracted, 0 if bit-mirrored. */
+ * bldfm_plan_last_march_mode: arithmetic of the plan's most recent march: 0 bit-mirrored, 1 FMA-contracted,
+ * 2 downward sweep. */
 int    bldfm_kappa(const bldfm_geometry *g, const bldfm_problem *prob, int32_t level, double *kappa);
 double bldfm_auto_kappa_limit(void);
 int    bldfm_plan_last_march_mode(const bldfm_plan *plan);

@@ -61,10 +61,8 @@ def leg_config3(torch, local, reps=5):
     out_f = torch.empty_like(out_c)
     d_src = torch.from_numpy(src).to(dev)
     flags = _lib.DOUBLE | _lib.OUT_ON_DEVICE | _lib.ASYNC | _lib.SRC_ON_DEVICE
-    if bldfm_b200.config.MARCH_MODE == "fma":
-        flags |= _lib.MARCH_FMA
-    elif bldfm_b200.config.MARCH_MODE == "auto":
-        flags |= _lib.MARCH_AUTO
+    flags |= {"exact": 0, "fma": _lib.MARCH_FMA, "sweep": _lib.MARCH_SWEEP,
+              "auto": _lib.MARCH_AUTO}[bldfm_b200.config.MARCH_MODE]
 
     def solve():
         _lib.check(L.bldfm_solve(plan, C.byref(prob), lvp, nlv, d_src.data_ptr(), flags, out_c.data_ptr(),
@@ -324,10 +322,8 @@ def leg_config4(torch, dist, rank, world, local, T=1440, reps=2, oracle_check=No
     dev_c = torch.empty((chunk, n, n), dtype=torch.float64, device=dev)
     dev_f = torch.empty_like(dev_c)
     flags = _lib.FOOTPRINT | _lib.DOUBLE | _lib.OUT_ON_DEVICE | _lib.ASYNC
-    if bldfm_b200.config.MARCH_MODE == "fma":
-        flags |= _lib.MARCH_FMA
-    elif bldfm_b200.config.MARCH_MODE == "auto":
-        flags |= _lib.MARCH_AUTO
+    flags |= {"exact": 0, "fma": _lib.MARCH_FMA, "sweep": _lib.MARCH_SWEEP,
+              "auto": _lib.MARCH_AUTO}[bldfm_b200.config.MARCH_MODE]
 
     def device_job():
         t0 = time.perf_counter()

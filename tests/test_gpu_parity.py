@@ -141,25 +141,27 @@ def _last_march_mode(B, kw):
 
 
 def test_config2_full_size_every_march_mode(B, oracle):
-    """BASELINE config 2 at FULL size in all three arithmetic modes: each within 1e-10 of the oracle; "auto"
-    (the default) picks the FMA-contracted march here (kappa = 7.1 <= 8.5) and is bit-identical to "fma"."""
+    """BASELINE config 2 at FULL size in every arithmetic mode: each within 1e-10 of the oracle; "auto" (the
+    default) picks the downward sweep here (kappa = 7.1 <= 8.5, one output level) and is bit-identical to "sweep"."""
     kw = _config2()
     _, oc, of = oracle.solve(nthreads=oracle.max_threads(), **kw)
     prev = B.config.MARCH_MODE
     got = {}
     try:
-        for mode in ("exact", "fma", "auto"):
+        for mode in ("exact", "fma", "sweep", "auto"):
             B.config.MARCH_MODE = mode
             _, conc, flx = B.steady_state_transport_solver(**kw)
             got[mode] = (conc, flx, _last_march_mode(B, kw))
             assert rel_l2(conc, oc) <= TOL_F64 and rel_l2(flx, of) <= TOL_F64, mode
     finally:
         B.config.MARCH_MODE = prev
-    assert got["exact"][2] == 0 and got["fma"][2] == 1 and got["auto"][2] == 1
-    assert np.array_equal(got["auto"][0], got["fma"][0]) and np.array_equal(got["auto"][1], got["fma"][1])
-    # the bit-mirrored march sits two orders of magnitude closer (1e-14 vs 1e-12)
+    assert got["exact"][2] == 0 and got["fma"][2] == 1 and got["sweep"][2] == 2 and got["auto"][2] == 2
+    assert np.array_equal(got["auto"][0], got["sweep"][0]) and np.array_equal(got["auto"][1], got["sweep"][1])
+    # the bit-mirrored march sits two orders of magnitude closer (1e-14 vs 1e-12): the fast modes differ from
+    # the reference by the reference's own round-off (SURVEY.md Appendix C: 3.7e-13 / 1.2e-12 here)
     assert rel_l2(got["exact"][1], of) <= 1e-13
     assert rel_l2(got["fma"][1], of) <= 1e-11
+    assert rel_l2(got["sweep"][1], of) <= 1e-11
 
 
 def test_auto_mode_falls_back_to_the_exact_march_when_ill_conditioned(B, oracle):
@@ -443,3 +445,100 @@ def test_baseline_config3_replica_against_oracle(B, oracle):
     # level by level as well (the upper levels carry little mass and would hide in the global norm)
     for l in range(nz + 1):
         assert rel_l2(f[l], of[l]) <= 1e-9, (l, rel_l2(f[l], of[l]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("deliver32", [False, True])
+def test_direct_host_stores_equal_the_copy_path(deliver32):
+    """BLDFM_OUT_MAPPED: the last transform pass writing the page-locked result itself gives the same bits as
+    device buffers + D2H copies (footprint and source mode, one and several levels)."""
+    import bldfm_b200
+    from bldfm_b200 import _lib
+    rng = np.random.default_rng(5)
+    z = np.linspace(0.5, 12.0, 24)
+    prof = (2.0 + 0.1 * z, 0.5 + 0.02 * z, 0.3 + 0.05 * z, 0.3 + 0.05 * z, 0.2 + 0.04 * z)
+    old = bldfm_b200.config.DELIVER_FLOAT32
+    bldfm_b200.config.DELIVER_FLOAT32 = deliver32
+    try:
+        for footprint, levels, q0 in ((True, 23, np.zeros((96, 128))), (False, [5, 11, 23], rng.random((64, 80)))):
+            got = []
+            for direct in (0, 64 << 20):
+                _lib.set_option("BLDFM_B200_DIRECT_HOST", direct)
+                _, c, f = bldfm_b200.steady_state_transport_solver(q0, z, prof, (300.0, 240.0), levels, modes=(64, 64),
+                                                                   meas_pt=(40.0, 30.0), footprint=footprint,
+                                                                   precision="double")
+                got.append((np.array(c), np.array(f)))
+            assert got[0][0].dtype == (np.float32 if deliver32 else np.float64)
+            assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
+            assert np.isfinite(got[1][0]).all() and np.abs(got[1][1]).max() > 0
+    finally:
+        _lib.set_option("BLDFM_B200_DIRECT_HOST", None)
+        bldfm_b200.config.DELIVER_FLOAT32 = old
+
+
+def _sweep_cases():
+    rng = np.random.default_rng(11)
+    z = np.concatenate([np.linspace(0.2, 10.0, 33), 10.0 + np.cumsum(np.linspace(0.5, 6.0, 20))])
+    u = 1.5 + 0.4 * np.log(z / 0.1)
+    prof = (u, 0.3 * u, 0.5 + 0.3 * z, 0.4 + 0.25 * z, 0.1 + 0.35 * z)
+    q0 = rng.random((96, 128))
+    return z, prof, q0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("footprint", [True, False])
+@pytest.mark.parametrize("level", [0, 17, 32, 52])
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_downward_sweep_equals_the_shooting_march(footprint, level, precision):
+    """MARCH_MODE="sweep" (one downward sweep from the radiation condition, march.cuh::sweep_body) against the
+    bit-mirrored shooting march: footprint and source mode (complex source spectrum, background concentration in
+    mode (0,0)), output level at the ground, inside, at the measurement height and at the top of the column,
+    shifted towers, both precisions.  The two differ by round-off only -- and that round-off is the shooting
+    march's (it grows with e^{2 kappa(level)}): the yardstick is therefore the difference
+    between the two SHOOTING marches (bit-mirrored and FMA-contracted), which the sweep must not exceed."""
+    import bldfm_b200 as B
+    z, prof, q0 = _sweep_cases()
+    kw = dict(srf_flx=q0, z=z, profiles=prof, domain=(1200.0, 900.0), levels=level, modes=(96, 64),
+              meas_pt=(310.0, 405.0), srf_bg_conc=0.0 if footprint else 0.7, footprint=footprint,
+              precision=precision)
+    prev = B.config.MARCH_MODE
+    got = {}
+    try:
+        for mode, code in (("exact", 0), ("fma", 1), ("sweep", 2)):
+            B.config.MARCH_MODE = mode
+            _, c, f = B.steady_state_transport_solver(**kw)
+            got[mode] = (np.array(c), np.array(f))
+            assert _last_march_mode(B, kw) == code
+    finally:
+        B.config.MARCH_MODE = prev
+    (c0, f0), (c1, f1), (c2, f2) = got["exact"], got["fma"], got["sweep"]
+    assert c2.dtype == c0.dtype and c2.shape == c0.shape
+    floor = 1e-13 if precision == "double" else 2e-7
+    assert rel_l2(c2, c0) <= max(floor, 4.0 * rel_l2(c1, c0)), (rel_l2(c2, c0), rel_l2(c1, c0))
+    assert rel_l2(f2, f0) <= max(floor, 4.0 * rel_l2(f1, f0)), (rel_l2(f2, f0), rel_l2(f1, f0))
+    assert rel_l2(c2, c0) <= 1e-9 and rel_l2(f2, f0) <= (1e-9 if precision == "double" else 1e-5)
+
+
+@pytest.mark.gpu
+def test_sweep_serves_one_level_and_never_overflows():
+    """Several output levels, or a column on which the swept vector could leave the binary64 range (here: 0.06 m
+    cells, growth bound e^4000), are marched upward (FMA-contracted) even when the sweep is asked for -- and "auto"
+    takes the bit-mirrored march there because the reference itself is round-off dominated."""
+    import bldfm_b200 as B
+    z, prof, q0 = _sweep_cases()
+    prev = B.config.MARCH_MODE
+    try:
+        B.config.MARCH_MODE = "sweep"
+        kw = dict(srf_flx=q0, z=z, profiles=prof, domain=(1200.0, 900.0), levels=[3, 17, 32], modes=(96, 64),
+                  footprint=False, precision="double")
+        _, c, f = B.steady_state_transport_solver(**kw)
+        assert _last_march_mode(B, kw) == 1 and c.shape == (3, 96, 128) and np.isfinite(c).all()
+        kw = dict(srf_flx=q0, z=z, profiles=prof, domain=(8.0, 6.0), levels=32, modes=(96, 64), footprint=True,
+                  precision="double")
+        _, c, f = B.steady_state_transport_solver(**kw)
+        assert _last_march_mode(B, kw) == 1
+        B.config.MARCH_MODE = "auto"
+        B.steady_state_transport_solver(**kw)
+        assert _last_march_mode(B, kw) == 0
+    finally:
+        B.config.MARCH_MODE = prev

@@ -1,5 +1,6 @@
-"""Calibration of BLDFM_MARCH_AUTO (needs a GPU): deviation of the FMA-contracted march from the oracle as a
-function of the conditioning number kappa, next to the bit-mirrored march.
+"""Calibration of BLDFM_MARCH_AUTO (needs a GPU): deviation of the fast marches (FMA-contracted shooting, downward
+sweep) from the oracle as a function of the conditioning number kappa, next to the
+bit-mirrored march.
 
 Footprint 512x512, n=64, unstable MOST, domains 1000 ... 16000 m (kappa 15 ... 3.5), plus stable / neutral
 profiles.  Prints one JSON line per case; the gate (bldfm_auto_kappa_limit, default 8.5) must keep every case
@@ -41,8 +42,8 @@ for name, dom, pk, wind in cases:
     kap = C.c_double(0.0)
     _lib.check(L.bldfm_kappa(C.byref(geom), C.byref(prob), 64, C.byref(kap)))
     out = {"case": name, "domain_m": dom, "kappa": round(kap.value, 3), "kappa_oracle": round(O.kappa(z, prof, O.geometry((512, 512), (dom, dom), (512, 512), None), float(z[64])), 3),
-           "auto_picks_fma": bool(kap.value <= limit)}
-    for mode in ("exact", "fma", "auto"):
+           "auto_picks_a_fast_march": bool(kap.value <= limit)}
+    for mode in ("exact", "fma", "sweep", "auto"):
         bldfm_b200.config.MARCH_MODE = mode
         _, c, f = bldfm_b200.steady_state_transport_solver(precision="double", **kw)
         out[f"{mode}_conc"] = rel_l2(c, oc)
