@@ -599,8 +599,9 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     const size_t sz_groups = (size_t)ngroups * sizeof(GroupDesc);
     const size_t off_towers = off_groups + sz_groups;
     const size_t sz_towers = (size_t)nprob * sizeof(TowerDesc);
-    const size_t off_rows = off_towers + sz_towers;
-    const size_t sz_rows = (size_t)nz_max * sizeof(int32_t);
+    // row_of is fetched by the march kernel with a bulk copy: 16-byte aligned, a multiple of 16 bytes long
+    const size_t off_rows = (off_towers + sz_towers + 15) & ~(size_t)15;
+    const size_t sz_rows = ((size_t)nz_max * sizeof(int32_t) + 15) & ~(size_t)15;
     const size_t sz_params = off_rows + sz_rows;
 
     Staging* st = nullptr;
@@ -625,7 +626,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
             }
         }
         memcpy(base + off_towers, towers.data(), sz_towers);
-        memcpy(base + off_rows, lp.row_of.data(), sz_rows);
+        memcpy(base + off_rows, lp.row_of.data(), (size_t)nz_max * sizeof(int32_t));
     }
     TRY(pl->params.ensure(sz_params));
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev[0], pl->stream));
@@ -735,7 +736,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
 
         const int64_t nthreads = march_thread_count(g.nlx, g.nly, ky0, rows, herm);
         const dim3 grid((unsigned)((nthreads + kMarchThreads - 1) / kMarchThreads), (unsigned)ngroups);
-        const size_t smem = (size_t)coef_stride * sizeof(LevelCoef) + (size_t)nz_max * sizeof(int32_t);
+        const size_t smem = (size_t)coef_stride * sizeof(LevelCoef) + sz_rows + 16;    // table | row_of | mbarrier
         if (smem > pl->smem_optin)
             return fail(BLDFM_ERR_INVALID, "nz too large for the shared-memory coefficient table (" +
                                                std::to_string(nz_max) + " levels)");

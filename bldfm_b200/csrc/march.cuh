@@ -350,6 +350,7 @@ __device__ __forceinline__ void sweep_body(const MarchArgs& a, const GroupDesc& 
     const double lx2 = lx * lx, ly2 = ly * ly;
     const int snap = a.snap_level;
     if (snap < 0 || snap > S) {                    // the requested level is never visited: rows stay zero
+        sc.ready();                                // (no CTA may retire while its bulk copy is in flight)
         for (int r = 0; r < a.nlv; ++r) emit(r, 0.0, 0.0, 0.0, 0.0);
         return;
     }
@@ -362,6 +363,8 @@ __device__ __forceinline__ void sweep_body(const MarchArgs& a, const GroupDesc& 
         csqrt_np(are, aim, er, ei);
         qr = gd.kz_top * er; qi = gd.kz_top * ei;
     }
+    sc.ready();
+    if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 1] = march_now();
     Prop P;
 #pragma unroll 4
     for (int i = S - 1; i >= snap; --i) {
@@ -402,8 +405,13 @@ __device__ __forceinline__ void sweep_body(const MarchArgs& a, const GroupDesc& 
 struct SmemCoef {
     const LevelCoef* sc;
     const int32_t* srow;
+    uint64_t* bar;       // mbarrier the bulk copy of the table completes on
     __device__ __forceinline__ const LevelCoef& operator[](int i) const { return sc[i]; }
     __device__ __forceinline__ int row(int i, const MarchArgs&) const { return srow[i]; }
+    // called once by every thread, after the table-independent part of its prologue and before the first
+    // table access: both bulk copies (table and row_of) have completed on the mbarrier.  Deliberately no
+    // CTA barrier here: the threads arrive from different branches (mode (0,0), sweep, shooting).
+    __device__ __forceinline__ void ready() const { mbar_wait(bar, 0); }
 };
 
 template <int ARITH, bool MULTI, class Coef>
@@ -413,7 +421,7 @@ __device__ __forceinline__ void march_body(const MarchArgs& a, const GroupDesc& 
     constexpr bool FMA = ARITH != 0;
     const int S = gd.S;
     ModeMap mm;
-    if (!march_map(a, tid, mm)) return;
+    if (!march_map(a, tid, mm)) return;      // (a thread that never reads the table need not wait for it)
     const int kx = mm.kx, ky = mm.ky;
     const double lx = a.lx[kx], ly = a.ly[ky];
 
@@ -449,10 +457,12 @@ __device__ __forceinline__ void march_body(const MarchArgs& a, const GroupDesc& 
         for (int r = visited; r < a.nlv; ++r)
             emit(r, (r == 0 && !any) ? gd.p000 : 0.0, 0.0, q0r, q0i);
     };
-    if (is00) { mode00(); return; }
+    if (is00) { sc.ready(); mode00(); return; }
     if (ARITH == 2 && !MULTI) { sweep_body(a, gd, emit, sc, lx, ly, q0r, q0i); return; }
 
     const double lx2 = lx * lx, ly2 = ly * ly;
+    sc.ready();
+    if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 1] = march_now();
 
     // IVP1 from (1,0), IVP2 from (0,q0)   (solver.py:220-226)
     double p1r = 1.0, p1i = 0.0, q1r = 0.0, q1i = 0.0;
@@ -553,22 +563,30 @@ k_march(const MarchArgs a)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     LevelCoef* sc = reinterpret_cast<LevelCoef*>(smem_raw);
     int32_t* srow = reinterpret_cast<int32_t*>(sc + a.coef_stride);
+    const uint32_t row_bytes = ((uint32_t)a.nrow_of * 4u + 15u) & ~15u;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(srow) + row_bytes);
 
     // the back-transform that follows may be launched as soon as every CTA of this grid is resident; its
     // CTAs start when ours retire and wait for the spectra in cudaGridDependencySynchronize()
     cudaTriggerProgrammaticLaunchCompletion();
     if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 0] = march_now();
     const GroupDesc gd = a.groups[blockIdx.y];
-    {
-        const double2* src = reinterpret_cast<const double2*>(a.coef + (size_t)blockIdx.y * a.coef_stride);
-        double2* dst = reinterpret_cast<double2*>(sc);
-        for (int i = threadIdx.x; i < gd.S * 8; i += kMarchThreads) dst[i] = src[i];
-        for (int i = threadIdx.x; i < a.nrow_of; i += kMarchThreads) srow[i] = a.row_of[i];
+    // The per-level table (S x 128 B) and row_of arrive by two bulk copies (cp.async.bulk -> mbarrier) issued by
+    // one thread; every thread runs the table-independent part of its prologue (mode map, wavenumbers, source
+    // spectrum, the tower's sincos, the top eigenvalue) meanwhile and waits in SmemCoef::ready().
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 1] = march_now();
-    march_body<ARITH, MULTI>(a, gd, a.towers + gd.tow_begin, SmemCoef{sc, srow},
-                           (int64_t)blockIdx.x * kMarchThreads + threadIdx.x);
+    if (threadIdx.x == 0) {
+        const uint32_t coef_bytes = (uint32_t)gd.S * (uint32_t)sizeof(LevelCoef);
+        mbar_expect_tx(bar, coef_bytes + row_bytes);
+        bulk_g2s(sc, a.coef + (size_t)blockIdx.y * a.coef_stride, coef_bytes, bar);
+        bulk_g2s(srow, a.row_of, row_bytes, bar);
+    }
+    march_body<ARITH, MULTI>(a, gd, a.towers + gd.tow_begin, SmemCoef{sc, srow, bar},
+                             (int64_t)blockIdx.x * kMarchThreads + threadIdx.x);
     if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 3] = march_now();
 }
 
