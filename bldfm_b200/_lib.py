@@ -52,7 +52,7 @@ EXPORTS = [
     "bldfm_memcpy_d2h", "bldfm_memcpy_h2d", "bldfm_fp64_peak",
     "bldfm_solve_batched_measure", "bldfm_sharded_stage1", "bldfm_sharded_stage2", "bldfm_ipc_export", "bldfm_ipc_open", "bldfm_ipc_close",
     "bldfm_march_coverage",
-    "bldfm_solve_batched_accumulate", "bldfm_kappa", "bldfm_auto_kappa_limit", "bldfm_plan_last_march_mode",
+    "bldfm_solve_batched_accumulate", "bldfm_kappa", "bldfm_sweep_admissible", "bldfm_auto_kappa_limit", "bldfm_plan_last_march_mode",
     "bldfm_device_memset", "bldfm_host_register", "bldfm_host_unregister",
     "bldfm_peer_signal", "bldfm_peer_wait", "bldfm_peer_status", "bldfm_plan_march_trace",
     "bldfm_plan_synchronize_previous", "bldfm_set_option", "bldfm_get_option",
@@ -151,6 +151,7 @@ def lib():
         "bldfm_ipc_close": (C.c_int, [C.c_int, vp]),
         "bldfm_solve_batched_accumulate": (C.c_int, [vp, i32, vp, I64P, i32, vp, C.c_int, vp, i32, vp, vp]),
         "bldfm_kappa": (C.c_int, [GP, PP, i32, _DP]),
+        "bldfm_sweep_admissible": (C.c_int, [GP, PP, i32, C.POINTER(C.c_int32)]),
         "bldfm_auto_kappa_limit": (dbl, []),
         "bldfm_plan_last_march_mode": (C.c_int, [vp]),
         "bldfm_device_memset": (C.c_int, [C.c_int, vp, C.c_int, i64]),

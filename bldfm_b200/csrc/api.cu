@@ -198,21 +198,30 @@ void fill_group(const bldfm_problem& pb, GroupDesc& gd)
     gd.pad = 0;
 }
 
-uint64_t fnv1a(const void* data, size_t n, uint64_t h)
+// word-wise multiplicative hash (the march de-duplication hashes ~5 KB per problem on the host thread that also
+// feeds the GPU; a byte-wise FNV cost 5 us per problem)
+uint64_t hash_words(const void* data, size_t n, uint64_t h)
 {
     const unsigned char* p = static_cast<const unsigned char*>(data);
-    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    size_t i = 0;
+    for (; i + 8 <= n; i += 8) {
+        uint64_t w;
+        memcpy(&w, p + i, 8);
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+    }
+    for (; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
     return h;
 }
 
 uint64_t problem_hash(const bldfm_problem& pb)
 {
     uint64_t h = 1469598103934665603ull;
-    h = fnv1a(&pb.nz, sizeof(pb.nz), h);
+    h = hash_words(&pb.nz, sizeof(pb.nz), h);
     const size_t nb = sizeof(double) * (size_t)pb.nz;
-    h = fnv1a(pb.z, nb, h); h = fnv1a(pb.u, nb, h); h = fnv1a(pb.v, nb, h);
-    h = fnv1a(pb.Kx, nb, h); h = fnv1a(pb.Ky, nb, h); h = fnv1a(pb.Kz, nb, h);
-    h = fnv1a(&pb.srf_bg_conc, sizeof(double), h);
+    h = hash_words(pb.z, nb, h); h = hash_words(pb.u, nb, h); h = hash_words(pb.v, nb, h);
+    h = hash_words(pb.Kx, nb, h); h = hash_words(pb.Ky, nb, h); h = hash_words(pb.Kz, nb, h);
+    h = hash_words(&pb.srf_bg_conc, sizeof(double), h);
     return h;
 }
 
@@ -246,13 +255,20 @@ double march_kappa(const bldfm_problem& pb, const bldfm_geometry& g, int level)
 // they hold for every mode: (1) |x| = |T| h^2 / Kz <= 1.5 on every level, which keeps det(M_i) = 1 + x^2/4 -
 // x^3/36 away from zero (|det - 1| <= 0.66) -- adj(M_i) is then a true multiple of the inverse; (2) the growth of
 // the swept vector, the size of its start value and the running product of determinants stay far inside the
-// binary64 range (|log| <= 600).
+// binary64 range (each within 2^+-512).
 bool sweep_admissible(const bldfm_problem& pb, const bldfm_geometry& g, int level)
 {
     const double lx = 2.0 * M_PI / (g.dx * g.nxe) * (g.nlx / 2.0);
     const double ly = 2.0 * M_PI / (g.dy * g.nye) * (g.nly / 2.0);
     const int S = pb.nz - 1;
-    double grow = 0.0, det_hi = 0.0, det_lo = 0.0;
+    // running products instead of sums of logarithms (this runs on the host in front of every launch); each is
+    // rescaled into [2^-512, 2^512] with its exponent counted, so neither can overflow on the way
+    double grow = 1.0, det_hi = 1.0, det_lo = 1.0;
+    int grow_e = 0, hi_e = 0, lo_e = 0;
+    auto renorm = [](double& v, int& e) {
+        if (v > 0x1p512) { v *= 0x1p-512; e += 512; }
+        else if (v < 0x1p-512) { v *= 0x1p512; e -= 512; }
+    };
     for (int i = 0; i < S; ++i) {
         const double kinv = 1.0 / pb.Kz[i];
         const double h = pb.z[i + 1] - pb.z[i];
@@ -262,18 +278,24 @@ bool sweep_admissible(const bldfm_problem& pb, const bldfm_geometry& g, int leve
         const double am = 1.0 + y;
         const double bm = kinv * h * (1.0 + y / 3.0);
         const double cm = T * h * (1.0 + y / 3.0);
-        grow += std::log(am + std::max(bm, cm));
+        grow *= am + std::max(bm, cm);
+        renorm(grow, grow_e);
         if (i < level) {
             const double e = y * y * (1.0 + 2.0 * y / 9.0);
-            det_hi += std::log1p(e);
-            det_lo += std::log1p(-e);
+            det_hi *= 1.0 + e;
+            det_lo *= 1.0 - e;
+            renorm(det_hi, hi_e);
+            renorm(det_lo, lo_e);
         }
     }
     const double kt = 1.0 / pb.Kz[S];
     const double lam = pb.Kz[S] * std::sqrt(std::hypot((pb.Kx[S] * lx * lx + pb.Ky[S] * ly * ly) * kt,
                                                          (std::fabs(pb.u[S]) * lx + std::fabs(pb.v[S]) * ly) * kt));
-    grow += std::log(std::max(1.0, lam));
-    return grow <= 600.0 && det_hi <= 600.0 && det_lo >= -600.0 && std::isfinite(grow);
+    grow *= std::max(1.0, lam);
+    renorm(grow, grow_e);
+    // |log| <= 600  <=>  within [e^-600, e^600] ~ 2^+-865: demand the counted exponents to stay at <= 512 in total
+    const auto within = [](double v, int e) { return std::isfinite(v) && v > 0.0 && e == 0; };
+    return within(grow, grow_e) && within(det_hi, hi_e) && within(det_lo, lo_e);
 }
 
 // kappa up to which BLDFM_MARCH_AUTO picks the FMA-contracted march.  The FMA march differs from the reference
@@ -630,9 +652,23 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     }
     TRY(pl->params.ensure(sz_params));
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev[0], pl->stream));
-    CUDA_TRY(cudaMemcpyAsync(pl->params.p, st->host, sz_params, cudaMemcpyHostToDevice, pl->stream));
-    CUDA_TRY(cudaEventRecord(st->done, pl->stream));
-    st->in_flight = true;
+    // small blocks with the march right behind them (footprint mode: no forward transform in between) are
+    // fetched by the device itself and the march is launched programmatically behind the fetch (transform.cuh)
+    const bool fetch = footprint && !analytic && sz_params <= ((size_t)64 << 10) && (sz_params % 16) == 0 &&
+                       fft_env_int("BLDFM_B200_PARAM_FETCH", 1) != 0;
+    if (fetch) {
+        const int n16 = (int)(sz_params / 16);
+        k_fetch_params<<<(n16 + 255) / 256, 256, 0, pl->stream>>>(static_cast<const uint4*>(st->host),
+                                                                   static_cast<uint4*>(pl->params.p), n16);
+        CUDA_TRY(cudaGetLastError());
+        pl->launches++;
+        // (the staging slot's "done" event is recorded behind the march: an event between the two kernels
+        // would serialise them)
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(pl->params.p, st->host, sz_params, cudaMemcpyHostToDevice, pl->stream));
+        CUDA_TRY(cudaEventRecord(st->done, pl->stream));
+        st->in_flight = true;
+    }
 
     NvtxRange nvtx_solve("bldfm_solve");
     // ---- K1-K3: spectrum of the padded source (non-footprint)
@@ -752,9 +788,15 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
             const bool multi = lp.visited > 1;
 #define LAUNCH_MARCH(F, M)                                                                          \
     do {                                                                                            \
-        CUDA_TRY(cudaFuncSetAttribute(k_march<F, M>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                      (int)pl->smem_optin));                                        \
-        k_march<F, M><<<grid, kMarchThreads, smem, pl->stream>>>(a);                                \
+        CUDA_TRY(set_max_dyn_smem(k_march<F, M>, (int)pl->smem_optin));                                        \
+        cudaLaunchConfig_t cfg = {};                                                                \
+        cfg.gridDim = grid; cfg.blockDim = dim3(kMarchThreads); cfg.dynamicSmemBytes = smem;        \
+        cfg.stream = pl->stream;                                                                    \
+        cudaLaunchAttribute at[1];                                                                  \
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                              \
+        at[0].val.programmaticStreamSerializationAllowed = (fetch && !pl->profiling) ? 1 : 0;       \
+        cfg.attrs = at; cfg.numAttrs = 1;                                                           \
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, k_march<F, M>, a));                                       \
     } while (0)
             if (arith == 2 && !multi) LAUNCH_MARCH(2, false);
             else if (fma_mode) { if (multi) LAUNCH_MARCH(1, true); else LAUNCH_MARCH(1, false); }
@@ -763,6 +805,10 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         }
         CUDA_TRY(cudaGetLastError());
         pl->launches++;
+        if (fetch) {
+            CUDA_TRY(cudaEventRecord(st->done, pl->stream));
+            st->in_flight = true;
+        }
     }
     if (pl->profiling) CUDA_TRY(cudaEventRecord(pl->ev[2], pl->stream));
 
@@ -1365,6 +1411,17 @@ int bldfm_kappa(const bldfm_geometry* g, const bldfm_problem* prob, int32_t leve
     return BLDFM_OK;
 }
 
+int bldfm_sweep_admissible(const bldfm_geometry* g, const bldfm_problem* prob, int32_t level, int32_t* ok)
+{
+    if (!g || !prob || !ok) return fail(BLDFM_ERR_INVALID, "NULL argument");
+    if (prob->nz < 2 || !prob->z || !prob->u || !prob->v || !prob->Kx || !prob->Ky || !prob->Kz)
+        return fail(BLDFM_ERR_INVALID, "need nz >= 2 and all profiles");
+    int lvl = level < 0 ? level + prob->nz : level;
+    if (lvl < 0 || lvl >= prob->nz) return fail(BLDFM_ERR_LEVEL_RANGE, "level out of range");
+    *ok = sweep_admissible(*prob, *g, lvl) ? 1 : 0;
+    return BLDFM_OK;
+}
+
 double bldfm_auto_kappa_limit(void) { return auto_kappa_limit(); }
 
 int bldfm_plan_march_trace(bldfm_plan* pl, uint64_t* host, int64_t max_ctas, int64_t* nctas)
@@ -1574,13 +1631,13 @@ int bldfm_march(int device, int64_t M, const double* p0, const double* q0, int32
         const size_t smem = sizeof(LevelCoef) * (size_t)S + sizeof(int32_t) * (size_t)nz;
         const unsigned grid = (unsigned)((M + kMarchThreads - 1) / kMarchThreads);
         if (flags & BLDFM_MARCH_FMA) {
-            MARCH_TRY(cudaFuncSetAttribute(k_ivp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            MARCH_TRY(set_max_dyn_smem(k_ivp<true>, 200 * 1024));
             k_ivp<true><<<grid, kMarchThreads, smem>>>(M, S, (const LevelCoef*)(d + off_lc), (const int32_t*)(d + off_row),
                 (const double2*)(d + off_p0), (const double2*)(d + off_q0), (const double*)(d + off_lx),
                 (const double*)(d + off_ly), (double2*)(d + off_pt), (double2*)(d + off_qt),
                 (double2*)(d + off_P), (double2*)(d + off_Q));
         } else {
-            MARCH_TRY(cudaFuncSetAttribute(k_ivp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            MARCH_TRY(set_max_dyn_smem(k_ivp<false>, 200 * 1024));
             k_ivp<false><<<grid, kMarchThreads, smem>>>(M, S, (const LevelCoef*)(d + off_lc), (const int32_t*)(d + off_row),
                 (const double2*)(d + off_p0), (const double2*)(d + off_q0), (const double*)(d + off_lx),
                 (const double*)(d + off_ly), (double2*)(d + off_pt), (double2*)(d + off_qt),

@@ -9,7 +9,34 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+#include <unordered_map>
+
 namespace bldfm {
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize once per (kernel, device, size) instead of in front of every launch
+// (a microsecond of driver time each, three times per solve, on the host path in front of the kernels).
+template <class K>
+inline cudaError_t set_max_dyn_smem(K kernel, int bytes)
+{
+    static std::mutex mu;
+    static std::unordered_map<uint64_t, int> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t key = (uint64_t)reinterpret_cast<uintptr_t>(reinterpret_cast<const void*>(kernel)) * 64u + (uint64_t)(dev & 63);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = done.find(key);
+        if (it != done.end() && it->second == bytes) return cudaSuccess;
+    }
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(mu);
+        done[key] = bytes;
+    }
+    return e;
+}
 
 // Per-level scalars of one march step i (solver.py:357-364), precomputed on the host in the
 // reference's operation order and staged in shared memory by the march kernels.

@@ -554,9 +554,9 @@ inline cudaError_t pruned_fft_launch(cudaStream_t stream, size_t smem_optin, con
 
     const size_t sx = fft_smem_bytes(ax.N, ax.cw, f32), sy = fft_smem_bytes(ay.N, ay.cw, f32);
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_fft_pass<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    e = set_max_dyn_smem(k_fft_pass<T, false, false>, (int)smem_optin);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_fft_pass<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    e = set_max_dyn_smem(k_fft_pass<T, false, true>, (int)smem_optin);
     if (e != cudaSuccess) return e;
 
     // gridDim.y is limited to 65535: split the field batch if needed
@@ -612,8 +612,7 @@ inline cudaError_t sharded_xpass(cudaStream_t stream, size_t smem_optin, const b
     ax.twiddle = tab.tw_x;
     ax.nfields_first = nfields;
     ax.in = spec_p; ax.in2 = spec_q; ax.out = send_p; ax.out2 = send_q;
-    cudaError_t e = cudaFuncSetAttribute(k_fft_pass<double, false, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    cudaError_t e = set_max_dyn_smem(k_fft_pass<double, false, false>, (int)smem_optin);
     if (e != cudaSuccess) return e;
     const dim3 grid((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), (unsigned)nfields);
     const int th = fft_pick_threads(ax.N, ax.cw, ax.radix[0]);
@@ -651,8 +650,7 @@ inline cudaError_t sharded_ypass(cudaStream_t stream, size_t smem_optin, const b
     ay.twiddle = tab.tw_y;
     ay.nfields_first = nfields;
     ay.in = recv_p; ay.in2 = recv_q; ay.out = out_p; ay.out2 = out_q;
-    cudaError_t e = cudaFuncSetAttribute(k_fft_pass<double, false, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    cudaError_t e = set_max_dyn_smem(k_fft_pass<double, false, true>, (int)smem_optin);
     if (e != cudaSuccess) return e;
     k_fft_pass<double, false, true><<<dim3((unsigned)((ay.ntrans + ay.cw - 1) / ay.cw), (unsigned)(2 * nfields)),
                                       fft_pick_threads(ay.N, ay.cw, ay.radix[0]),
@@ -692,9 +690,9 @@ inline cudaError_t pruned_fft_forward(cudaStream_t stream, size_t smem_optin, co
     ay.nfields_first = 1; ay.in = work; ay.in2 = work; ay.out = spec; ay.out2 = spec; ay.twiddle = tab.tw_y;
 
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_fft_pass<double, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    e = set_max_dyn_smem(k_fft_pass<double, true, false>, (int)smem_optin);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_fft_pass<double, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    e = set_max_dyn_smem(k_fft_pass<double, false, false>, (int)smem_optin);
     if (e != cudaSuccess) return e;
     if (!skip_x) {     // `work` already holds the x-pass when a second row range of the same source is asked for
         k_fft_pass<double, true, false><<<dim3((unsigned)((ax.ntrans + ax.cw - 1) / ax.cw), 1),

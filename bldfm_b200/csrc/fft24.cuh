@@ -366,8 +366,7 @@ inline cudaError_t fft24_launch_pass(cudaStream_t stream, size_t smem_optin, int
     const int threads = std::min(tmax, std::max(96, (items + 31) / 32 * 32));
 #define BLDFM_FFT24_CASE(LQ)                                                                                  \
     case LQ: {                                                                                                \
-        cudaError_t e = cudaFuncSetAttribute(k_fft24<T, PASS, LQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem_optin);                                                \
+        cudaError_t e = set_max_dyn_smem(k_fft24<T, PASS, LQ>, (int)smem_optin);                                                \
         if (e != cudaSuccess) return e;                                                                       \
         cudaLaunchConfig_t cfg = {};                                                                          \
         cfg.gridDim = grid; cfg.blockDim = dim3((unsigned)threads); cfg.dynamicSmemBytes = sm; cfg.stream = stream; \

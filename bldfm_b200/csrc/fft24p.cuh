@@ -333,8 +333,7 @@ inline cudaError_t fft24p_launch_pass(cudaStream_t stream, size_t smem_optin, in
     const int threads = (PASS == 0 && lq >= 7 && lq <= 8) ? 192 : kFft24Threads;
 #define BLDFM_FFT24P_CASE(LQ)                                                                                  \
     case LQ: {                                                                                                 \
-        cudaError_t e = cudaFuncSetAttribute(k_fft24p<T, PASS, LQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem_optin);                                                 \
+        cudaError_t e = set_max_dyn_smem(k_fft24p<T, PASS, LQ>, (int)smem_optin);                                                 \
         if (e != cudaSuccess) return e;                                                                        \
         cudaLaunchConfig_t cfg = {};                                                                           \
         cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)threads);                            \

@@ -294,11 +294,11 @@ inline cudaError_t fft48_launch_pass(cudaStream_t stream, size_t smem_optin, int
     cfg.attrs = at; cfg.numAttrs = 1;
     cudaError_t e;
     if (lq == 5) {
-        e = cudaFuncSetAttribute(k_fft48<T, PASS, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+        e = set_max_dyn_smem(k_fft48<T, PASS, 5>, (int)smem_optin);
         if (e != cudaSuccess) return e;
         e = cudaLaunchKernelEx(&cfg, k_fft48<T, PASS, 5>, a);
     } else if (lq == 4) {
-        e = cudaFuncSetAttribute(k_fft48<T, PASS, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+        e = set_max_dyn_smem(k_fft48<T, PASS, 4>, (int)smem_optin);
         if (e != cudaSuccess) return e;
         e = cudaLaunchKernelEx(&cfg, k_fft48<T, PASS, 4>, a);
     } else {

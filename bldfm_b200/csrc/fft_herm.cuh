@@ -443,9 +443,9 @@ inline cudaError_t herm_fft_launch(cudaStream_t stream, size_t smem_optin, const
     ay.twiddle = tab.tw_y; ay.rev = tab.rev_y; ay.tw24 = tab.t24_y; ay.tw48 = tab.t48_y;
 
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_fft_h<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    e = set_max_dyn_smem(k_fft_h<T, 0>, (int)smem_optin);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_fft_h<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    e = set_max_dyn_smem(k_fft_h<T, 1>, (int)smem_optin);
     if (e != cudaSuccess) return e;
     const int64_t chunk = 16384;
     for (int64_t f0 = 0; f0 < nfields; f0 += chunk) {
@@ -497,7 +497,7 @@ inline cudaError_t herm_sharded_xpass(cudaStream_t stream, size_t smem_optin, co
     ax.out_block_stride = (int64_t)Rp * nxl;
     ax.nfields_first = nfields;
     ax.in = spec_p; ax.in2 = spec_q; ax.out = send_p; ax.out2 = send_q;
-    cudaError_t e = cudaFuncSetAttribute(k_fft_h<double, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    cudaError_t e = set_max_dyn_smem(k_fft_h<double, 0>, (int)smem_optin);
     if (e != cudaSuccess) return e;
     ax.hs = 1;                                             // the sharded march is always the half-plane one
     const int lqx = fft_env_int("BLDFM_B200_FFT24", 1) ? fft24_lq(g.nfx, g.nlx, g.nx, g.px) : -1;
@@ -537,7 +537,7 @@ inline cudaError_t herm_sharded_ypass(cudaStream_t stream, size_t smem_optin, co
     ay.twiddle = tab.tw_y; ay.rev = tab.rev_y; ay.tw24 = tab.t24_y; ay.tw48 = tab.t48_y;
     ay.nfields_first = nfields;
     ay.in = recv_p; ay.in2 = recv_q; ay.out = out_p; ay.out2 = out_q;
-    cudaError_t e = cudaFuncSetAttribute(k_fft_h<double, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_optin);
+    cudaError_t e = set_max_dyn_smem(k_fft_h<double, 1>, (int)smem_optin);
     if (e != cudaSuccess) return e;
     const int lqy = fft_env_int("BLDFM_B200_FFT24", 1) ? fft24_lq(g.nfy, g.nly, g.ny, g.py) : -1;
     e = herm_launch_pass<double, 1>(stream, smem_optin, lqy, ay, (unsigned)(2 * nfields), (int64_t)ay.ntrans * 2 * nfields);

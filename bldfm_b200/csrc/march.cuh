@@ -570,6 +570,9 @@ k_march(const MarchArgs a)
     // CTAs start when ours retire and wait for the spectra in cudaGridDependencySynchronize()
     cudaTriggerProgrammaticLaunchCompletion();
     if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 0] = march_now();
+    // the parameter block may still be on its way (k_fetch_params in front of a programmatic launch); a no-op
+    // for an ordinary launch
+    cudaGridDependencySynchronize();
     const GroupDesc gd = a.groups[blockIdx.y];
     // The per-level table (S x 128 B) and row_of arrive by two bulk copies (cp.async.bulk -> mbarrier) issued by
     // one thread; every thread runs the table-independent part of its prologue (mode map, wavenumbers, source

@@ -137,4 +137,17 @@ k_downcast2(const double* __restrict__ a, const double* __restrict__ b, float* _
     }
 }
 
+// The per-solve parameter block of a single solve (13.8 KB at config 2) fetched from the page-locked staging buffer
+// by the device itself instead of a copy-engine H2D copy: the march behind it is launched with programmatic
+// dependent launch, so its CTAs are resident and past their table-independent prologue set-up when the block
+// lands (cudaGridDependencySynchronize in k_march) -- a copy followed by a kernel costs ~8 us on the stream,
+// this pair ~3.
+__global__ void __launch_bounds__(256)
+k_fetch_params(const uint4* __restrict__ src_mapped_host, uint4* __restrict__ dst, int n16)
+{
+    cudaTriggerProgrammaticLaunchCompletion();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x)
+        dst[i] = src_mapped_host[i];
+}
+
 }  // namespace bldfm

@@ -193,6 +193,10 @@ int  bldfm_solve_batched_accumulate(bldfm_plan *plan, int32_t nprob, const bldfm
  * bldfm_plan_last_march_mode: arithmetic of the plan's most recent march: 0 bit-mirrored, 1 FMA-contracted,
  * 2 downward sweep. */
 int    bldfm_kappa(const bldfm_geometry *g, const bldfm_problem *prob, int32_t level, double *kappa);
+/* May the downward sweep (BLDFM_MARCH_SWEEP) serve this problem at output level `level`?  *ok = 1 where neither the
+ * swept vector nor the determinant product can leave the binary64 range and no step can be singular (bounds at the
+ * largest retained wavenumbers; pure host arithmetic).  Where it is 0 the FMA-contracted shooting march runs. */
+int    bldfm_sweep_admissible(const bldfm_geometry *g, const bldfm_problem *prob, int32_t level, int32_t *ok);
 double bldfm_auto_kappa_limit(void);
 int    bldfm_plan_last_march_mode(const bldfm_plan *plan);
 

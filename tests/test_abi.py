@@ -172,3 +172,34 @@ def test_make_grid_modes_match_the_reference_meshgrid():
             ro = make_grid(z, lv, (100.0, 60.0), nx, ny, mode="0")
             with pytest.raises(ValueError):
                 ro[0][...] = 1.0
+
+
+def test_sweep_admissibility_bounds():
+    """bldfm_sweep_admissible (host arithmetic in front of every BLDFM_MARCH_SWEEP / AUTO launch): BASELINE
+    configs 2 and 5 (same dx and wavenumber range) are admissible at every level; a column whose swept vector
+    would grow beyond 2^512 (centimetre cells), a step with |T| h^2 / Kz > 1.5, and degenerate profiles are not."""
+    from bldfm_b200 import _lib
+    from bldfm_b200.pbl_model import vertical_profiles
+    lib = _lib.lib()
+
+    def ok(shape, domain, modes, z, prof, lvl):
+        geom = _lib.geometry(shape, domain, modes, None)
+        prob, keep = _lib.make_problem(z, prof, (0.0, 0.0), 0.0)
+        out = C.c_int32(-1)
+        assert lib.bldfm_sweep_admissible(C.byref(geom), C.byref(prob), lvl, C.byref(out)) == 0
+        return out.value
+
+    z, prof = vertical_profiles(64, 10.0, (-3.0, -4.0), ustar=0.4, mol=-50.0)
+    for lvl in (0, 1, 64, len(z) - 1):
+        assert ok((512, 512), (4000.0, 4000.0), (512, 512), z, prof, lvl) == 1
+    z5, prof5 = vertical_profiles(256, 10.0, (-3.0, -4.0), ustar=0.4, mol=-50.0)
+    assert ok((4096, 4096), (32000.0, 32000.0), (4096, 4096), z5, prof5, 256) == 1
+    # 4 cm cells: growth exponent of the column far beyond 355
+    assert ok((512, 512), (20.0, 20.0), (512, 512), z, prof, 64) == 0
+    # one coarse step: |T| h^2 / Kz > 1.5 at the largest wavenumber
+    zc = np.array([0.0, 1.0, 2.0, 12.0])
+    one = np.ones(4)
+    assert ok((64, 64), (640.0, 640.0), (64, 64), zc, (2 * one, one, one, one, 0.5 * one), 2) == 0
+    assert ok((64, 64), (64000.0, 64000.0), (64, 64), zc, (2 * one, one, one, one, 0.5 * one), 2) == 1
+    # non-increasing heights are refused rather than swept
+    assert ok((64, 64), (64000.0, 64000.0), (64, 64), np.array([0.0, 1.0, 1.0, 3.0]), (one, one, one, one, one), 2) == 0
