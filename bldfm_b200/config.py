@@ -45,3 +45,7 @@ MAX_WORKSPACE_BYTES = int(os.environ.get("BLDFM_B200_MAX_WORKSPACE", str(64 << 3
 # bytes over PCIe -- the device->host copy is the largest part of a single solve's end-to-end time).  Changes
 # the result dtype, hence off by default.
 DELIVER_FLOAT32 = os.environ.get("BLDFM_B200_DELIVER_F32", "0") == "1"
+# run_bldfm_parallel under torchrun, every field delivered to rank 0's host memory: size the ranks' shares by their
+# measured host-link rates (distributed.link_rates; the GPUs of a box need not share the host links evenly)
+# instead of equally.  Off by default.
+LINK_AWARE_SHARDING = os.environ.get("BLDFM_B200_LINK_AWARE", "0") == "1"

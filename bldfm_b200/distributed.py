@@ -55,20 +55,72 @@ def pin_to_local_cores(local_rank=None, local_world=None):
     return mine
 
 
-def shard_groups(keys: Sequence[Hashable], costs: Sequence[float], world_size: int) -> List[List[int]]:
+def shard_groups(keys: Sequence[Hashable], costs: Sequence[float], world_size: int,
+                 speeds: Sequence[float] = None) -> List[List[int]]:
     """Assign group indices to ranks: longest-processing-time greedy on `costs`, ties by index.
 
-    Deterministic (every rank computes the same assignment without communicating).
-    Returns ``assign[rank] = sorted list of group indices``.
+    ``speeds`` (optional, one positive number per rank, the same on every rank): relative rate at which a rank
+    works its share off -- e.g. its host-link bandwidth when every result is delivered to the host; a group goes
+    to the rank that would finish it first.  Deterministic (every rank computes the same assignment without
+    communicating).  Returns ``assign[rank] = sorted list of group indices``.
     """
+    if speeds is None:
+        speeds = [1.0] * world_size
+    if len(speeds) != world_size or not all(float(v) > 0.0 for v in speeds):
+        raise ValueError("speeds must hold one positive number per rank")
     order = sorted(range(len(keys)), key=lambda i: (-float(costs[i]), i))
     load = [0.0] * world_size
     assign: List[List[int]] = [[] for _ in range(world_size)]
     for i in order:
-        r = min(range(world_size), key=lambda k: (load[k], k))
+        c = float(costs[i])
+        r = min(range(world_size), key=lambda k: ((load[k] + c) / float(speeds[k]), k))
         assign[r].append(i)
-        load[r] += float(costs[i])
+        load[r] += c
     return [sorted(a) for a in assign]
+
+
+_LINK_RATES = {}
+
+
+def link_rates(nbytes: int = 128 << 20):
+    """Device->host copy rate of every rank into page-locked memory while ALL ranks copy at once (GB/s, the same
+    list on every rank; measured once per process and world size, ~10 ms).  On a box whose GPUs do not share the
+    host links evenly (measured on this pool: 11.6 GB/s for four of eight GPUs, 18.6 GB/s for the other four,
+    profiles/r2_d2h_shared_probe_n8.json) these are the speeds a delivered-to-host job should be sharded by."""
+    rank, ws = world()
+    if ws in _LINK_RATES:
+        return _LINK_RATES[ws]
+    import ctypes as C
+    import time
+    from . import _lib, config
+    import torch
+    import torch.distributed as dist
+    L = _lib.lib()
+    dev, host = C.c_void_p(), C.c_void_p()
+    _lib.check(L.bldfm_device_alloc(config.DEVICE, nbytes, C.byref(dev)))
+    try:
+        _lib.check(L.bldfm_host_alloc(nbytes, C.byref(host)))
+        try:
+            best = 0.0
+            for rep in range(3):                      # first repetition warms the buffers up
+                if ws > 1:
+                    dist.barrier()
+                t0 = time.perf_counter()
+                _lib.check(L.bldfm_memcpy_d2h(config.DEVICE, host, dev, nbytes))
+                dt = time.perf_counter() - t0
+                if rep:
+                    best = max(best, nbytes / dt * 1e-9)
+        finally:
+            L.bldfm_host_free(host)
+    finally:
+        L.bldfm_device_free(config.DEVICE, dev)
+    if ws > 1:
+        out = [None] * ws
+        dist.all_gather_object(out, float(best))
+    else:
+        out = [float(best)]
+    _LINK_RATES[ws] = [max(float(v), 1e-3) for v in out]
+    return _LINK_RATES[ws]
 
 
 def owner_of_tasks(task_group: Sequence[int], assign: List[List[int]]) -> np.ndarray:

@@ -23,6 +23,7 @@ from typing import Dict, List, Sequence, Tuple
 import numpy as np
 
 from . import _lib
+from . import config as _cfg
 from . import distributed as _dist
 from .pbl_model import ProfileBatch, compute_wind_fields_batch, vertical_profiles, vertical_profiles_batch
 from .solver import (FieldAccumulator, make_grid, measure_batched, solve_batched, steady_state_transport_solver,
@@ -324,15 +325,27 @@ def run_bldfm_multitower(config, surface_flux=None) -> dict:
     return out
 
 
-def _shard(config, tasks):
-    """(rank, world, owner[t], my task indices): march groups spread over the ranks (distributed.shard_groups)."""
+def _shard(config, tasks, delivered=False):
+    """(rank, world, owner[t], my task indices): march groups spread over the ranks (distributed.shard_groups).
+
+    ``delivered``: every field of the job goes to host memory, so with more than one rank the job is bound by
+    the host links -- and those need not be equal for all GPUs of a box.  With ``config.LINK_AWARE_SHARDING``
+    (``BLDFM_B200_LINK_AWARE=1``) the shares are then sized by the measured per-rank link rates
+    (``distributed.link_rates``) and by the bytes a group delivers instead of by its compute cost."""
     rank, ws = _dist.world()
     keys, task_group = plan_tasks(config, tasks)
     ntow = np.bincount(task_group, minlength=len(keys))
-    assign = _dist.shard_groups(keys, 1.0 + 0.15 * ntow, ws)     # march dominates, towers add a little
+    if delivered and ws > 1 and _cfg.LINK_AWARE_SHARDING:
+        assign = _dist.shard_groups(keys, ntow.astype(float), ws, speeds=_dist.link_rates())
+    else:
+        assign = _dist.shard_groups(keys, 1.0 + 0.15 * ntow, ws)     # march dominates, towers add a little
     owner = _dist.owner_of_tasks(task_group, assign)
     mine = [t for t in range(len(tasks)) if owner[t] == rank]
     return rank, ws, owner, mine
+
+
+# wall-clock phases of this rank's most recent gathering run_bldfm_parallel call (diagnostics; bench.py reports them)
+LAST_PARALLEL_PHASES = {}
 
 
 def run_bldfm_parallel(config, max_workers=None, parallel_over: str = "towers", surface_flux=None,
@@ -358,7 +371,7 @@ def run_bldfm_parallel(config, max_workers=None, parallel_over: str = "towers", 
     n = config.met.n_timesteps
     towers = config.towers
     tasks = _multitower_tasks(config)
-    rank, ws, owner, mine = _shard(config, tasks)
+    rank, ws, owner, mine = _shard(config, tasks, delivered=gather)
     out = {t.name: [None] * n for t in towers}
     if not gather:
         local = solve_tasks(config, [tasks[t] for t in mine], None, None)
@@ -372,8 +385,13 @@ def run_bldfm_parallel(config, max_workers=None, parallel_over: str = "towers", 
     nlv = 1 if np.ndim(lv) == 0 else len(lv)
     dom = config.domain
     counts = np.bincount(owner, minlength=ws)
+    import time as _time
+    t_start = _time.perf_counter()
     seg = _dist.SharedResults.acquire((nlv, dom.ny, dom.nx), counts)
     conc_l, flx_l = seg.local_block()
+    phases = LAST_PARALLEL_PHASES
+    phases.clear()
+    phases["acquire_segment_s"] = _time.perf_counter() - t_start
 
     # Rank 0 builds the result dictionaries (views into the segment, valid objects whatever the bytes are yet)
     # on a helper thread WHILE the GPUs solve and copy: its main thread spends that phase blocked in CUDA waits
@@ -421,12 +439,19 @@ def run_bldfm_parallel(config, max_workers=None, parallel_over: str = "towers", 
         builder = threading.Thread(target=build, name="bldfm-result-builder")
         builder.start()
     try:
+        t0 = _time.perf_counter()
         solve_tasks(config, [tasks[t] for t in mine], None, None, out=(conc_l, flx_l), out_pinned=seg.pinned,
                     build_results=False)
+        phases["solve_and_copy_s"] = _time.perf_counter() - t0
+        t0 = _time.perf_counter()
         seg.barrier()                                  # every rank's fields have landed in the segment
+        phases["wait_for_other_ranks_s"] = _time.perf_counter() - t0
     finally:
+        t0 = _time.perf_counter()
         if builder is not None:
             builder.join()
+        phases["wait_for_result_builder_s"] = _time.perf_counter() - t0
+        phases["total_s"] = _time.perf_counter() - t_start
     if rank != 0:
         return {}
     if failure:

@@ -209,22 +209,28 @@ def host_link_probe(torch, dist, rank, world, local, nbytes=256 << 20):
     d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
 
-    def bw():
+    def bw(aligned):
         best = 0.0
         for _ in range(3):
+            if aligned:
+                # every repetition starts on all ranks at once: otherwise a rank that is late copies alone and
+                # reports the rate of an idle link (the GPUs of a box need not share the host links evenly:
+                # profiles/r2_d2h_shared_probe_n8.json)
+                _barrier(torch, dist, world)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            h.copy_(d, non_blocking=True)
+            for _ in range(2):
+                h.copy_(d, non_blocking=True)
             e1.record()
             torch.cuda.synchronize()
-            best = max(best, nbytes / (e0.elapsed_time(e1) * 1e-3) * 1e-9)
+            best = max(best, 2 * nbytes / (e0.elapsed_time(e1) * 1e-3) * 1e-9)
         return best
 
     h.copy_(d)
     _barrier(torch, dist, world)
-    alone = bw() if rank == 0 else 0.0
+    alone = bw(False) if rank == 0 else 0.0
     _barrier(torch, dist, world)
-    together = bw()
+    together = bw(True)
     t = torch.tensor([together], dtype=torch.float64, device=dev)
     tmin = t.clone()
     if world > 1:
@@ -235,7 +241,8 @@ def host_link_probe(torch, dist, rank, world, local, nbytes=256 << 20):
         dist.all_reduce(a, op=dist.ReduceOp.MAX)
     return {"d2h_gbs_one_gpu_alone": float(a.item()), "d2h_gbs_all_gpus_together_aggregate": float(t.item()),
             "d2h_gbs_all_gpus_together_min_per_gpu": float(tmin.item()), "bytes_per_copy": nbytes,
-            "note": "pinned host memory, CUDA events; the aggregate is the ceiling of every delivered-to-host number"}
+            "note": "pinned host memory, CUDA events, repetitions start on all ranks at once; the aggregate is the "
+                    "ceiling of every delivered-to-host number"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -354,11 +361,18 @@ def leg_config4(torch, dist, rank, world, local, T=1440, reps=2, oracle_check=No
     # ---- delivered: run_bldfm_parallel, every footprint in host memory of rank 0, gather inside the timing
     interface.run_bldfm_parallel(cfg, parallel_over="both")            # warm-up: creates + page-locks the segment
     dt, full = timed(lambda: interface.run_bldfm_parallel(cfg, parallel_over="both"), reps)
+    phases = dict(interface.LAST_PARALLEL_PHASES)                     # of the last repetition, per rank
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, phases)
+    else:
+        gathered = [phases]
     link = host_link if host_link is not None else host_link_probe(torch, dist, rank, world, local)
     res["host_link"] = link
     res["delivered"] = {"s": dt, "footprints_per_s": nfoot / dt, "bytes_to_host": need,
                         "host_gbs": need / dt * 1e-9,
                         "frac_of_host_link": need / dt * 1e-9 / max(link["d2h_gbs_all_gpus_together_aggregate"], 1e-9),
+                        "phases_by_rank_last_rep": [{k: round(v, 4) for k, v in p.items()} for p in gathered],
                         "api": "bldfm_b200.run_bldfm_parallel(cfg, parallel_over='both'): result dict of every (tower, "
                                "timestep) on rank 0; each rank copies device->host over its own PCIe link into a "
                                "page-locked shared-memory segment; wall clock, barrier-bracketed, max over ranks"}

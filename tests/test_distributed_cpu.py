@@ -166,3 +166,46 @@ def test_run_bldfm_parallel_without_process_group_uses_a_local_segment(monkeypat
     r3 = interface.run_bldfm_parallel(cfg)
     assert {id(s) for s in SharedResults._cache.values()} == seg_ids      # the freed segment was reused
     assert np.array_equal(r3["C"][4]["flx"], expect[-1]["flx"])
+
+
+def test_shard_groups_by_rank_speed():
+    """Weighted LPT: a rank that works its share off 1.6x faster gets 1.6x the groups; equal speeds reproduce the
+    unweighted assignment; the result is deterministic and covers every group once."""
+    from bldfm_b200.distributed import shard_groups
+    keys = list(range(1440))
+    costs = [8.0] * 1440
+    speeds = [11.6] * 4 + [18.6] * 4
+    a = shard_groups(keys, costs, 8, speeds=speeds)
+    assert sorted(g for r in a for g in r) == keys
+    n = [len(r) for r in a]
+    assert max(n[:4]) - min(n[:4]) <= 1 and max(n[4:]) - min(n[4:]) <= 1
+    assert abs(n[4] / n[0] - 18.6 / 11.6) < 0.03
+    finish = [8.0 * n[r] / speeds[r] for r in range(8)]
+    assert max(finish) / min(finish) < 1.02
+    assert a == shard_groups(keys, costs, 8, speeds=speeds)
+    assert shard_groups(keys, costs, 8) == shard_groups(keys, costs, 8, speeds=[3.0] * 8)
+    with pytest.raises(ValueError):
+        shard_groups(keys, costs, 8, speeds=[1.0] * 7)
+    with pytest.raises(ValueError):
+        shard_groups(keys, costs, 2, speeds=[1.0, 0.0])
+
+
+def test_link_aware_shares_of_a_delivered_job(monkeypatch):
+    """interface._shard(delivered=True) with config.LINK_AWARE_SHARDING: shares follow the per-rank link rates and
+    the bytes a group delivers; compute-bound jobs (delivered=False) and the default keep the equal split."""
+    import bldfm_b200
+    from bldfm_b200 import distributed as D, interface
+    from scripts.bench_legs import config4
+    cfg = config4(96, 8, 64)
+    tasks = interface._multitower_tasks(cfg)
+    monkeypatch.setattr(D, "world", lambda: (1, 4))
+    monkeypatch.setattr(D, "link_rates", lambda: [10.0, 10.0, 20.0, 20.0])
+    monkeypatch.setattr(bldfm_b200.config, "LINK_AWARE_SHARDING", False)
+    _, ws, owner, mine = interface._shard(cfg, tasks, delivered=True)
+    assert ws == 4 and np.bincount(owner, minlength=4).tolist() == [192] * 4
+    monkeypatch.setattr(bldfm_b200.config, "LINK_AWARE_SHARDING", True)
+    _, _, owner, mine = interface._shard(cfg, tasks, delivered=True)
+    assert np.bincount(owner, minlength=4).tolist() == [128, 128, 256, 256]
+    assert mine == [t for t in range(len(tasks)) if owner[t] == 1]
+    _, _, owner, _ = interface._shard(cfg, tasks, delivered=False)
+    assert np.bincount(owner, minlength=4).tolist() == [192] * 4
