@@ -167,3 +167,36 @@ def test_reference_spectra_are_conjugate_symmetric(oracle, shape, modes):
                 assert np.array_equal(tq[:, my, mx], np.conj(tq[:, ky, kx]))
                 checked += 1
     assert checked >= (nlx - 1) * (nly - 1)
+
+
+def test_downward_sweep_is_the_same_discrete_solution_as_linear_shooting(oracle):
+    """The identity behind MARCH_MODE="sweep" (bldfm_b200/csrc/march.cuh::sweep_body), on the CPU: one vector swept
+    downward from the radiation condition with adj(M_i), scaled by q0 * prod_{i<L} det(M_i) / (w_0).q, is the
+    solution the reference's two upward IVPs + alpha produce (solver.py:220-235).  In extended precision the two
+    agree to round-off; in binary64 the sweep stays at 1e-15 while shooting carries the e^{2 kappa} round-off of
+    SURVEY.md Appendix C (1e-12 at kappa = 7.1, 1e-10 at kappa = 10.3)."""
+    import importlib.util
+    from conftest import ROOT
+    O = oracle
+    spec = importlib.util.spec_from_file_location("sweep_accuracy", ROOT / "tests" / "tools" / "sweep_accuracy.py")
+    sa = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sa)
+    from bldfm_b200.pbl_model import vertical_profiles
+    rng = np.random.default_rng(3)
+    rel = lambda a, b: float(np.linalg.norm(np.asarray(a - b, np.clongdouble)) / np.linalg.norm(b))  # noqa: E731
+    for dom, shoot_lo, shoot_hi in ((4000.0, 1e-13, 2e-11), (2000.0, 5e-12, 2e-9)):
+        z, prof = vertical_profiles(64, 10.0, (-3.0, -4.0), ustar=0.4, mol=-50.0)
+        g = O.geometry((512, 512), (dom, dom), (512, 512), None)
+        lx, ly = O.wavenumbers(g)
+        ix = rng.integers(1, 512, 600)
+        iy = rng.integers(0, 512, 600)
+        a = (z, prof, g, lx, ly, ix, iy, 64)
+        tp, tq = sa.run(np.longdouble, np.clongdouble, True, *a)
+        xp, xq = sa.run(np.longdouble, np.clongdouble, False, *a)
+        fp, fq = sa.run(np.float64, np.complex128, False, *a)
+        sp, sq = sa.run(np.float64, np.complex128, True, *a)
+        if np.finfo(np.longdouble).nmant > 52:                       # x87 extended precision available
+            assert rel(xp, tp) <= 1e-12 and rel(xq, tq) <= 1e-12     # same discrete solution
+            assert rel(sp, tp) <= 2e-14 and rel(sq, tq) <= 2e-14     # the sweep does not amplify round-off
+            assert shoot_lo <= rel(fq, tq) <= shoot_hi               # shooting does, by e^{2 kappa}
+        assert rel(sp, fp) <= shoot_hi and rel(sq, fq) <= shoot_hi   # binary64 against binary64
