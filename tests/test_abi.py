@@ -203,3 +203,20 @@ def test_sweep_admissibility_bounds():
     assert ok((64, 64), (64000.0, 64000.0), (64, 64), zc, (2 * one, one, one, one, 0.5 * one), 2) == 1
     # non-increasing heights are refused rather than swept
     assert ok((64, 64), (64000.0, 64000.0), (64, 64), np.array([0.0, 1.0, 1.0, 3.0]), (one, one, one, one, one), 2) == 0
+
+
+def test_flag_and_status_constants_match_the_header():
+    """Every `#define BLDFM_<NAME> <value>` of include/bldfm_b200.h has the same value in the ctypes binding
+    (flags as `_lib.<NAME>`, status codes as `_lib.<NAME>`), flags are distinct bits, and nothing is missing."""
+    import re
+    from bldfm_b200 import _lib
+    text = (ROOT / "include" / "bldfm_b200.h").read_text()
+    defs = {m.group(1): int(m.group(2), 0)
+            for m in re.finditer(r"^#define\s+BLDFM_([A-Z0-9_]+)\s+(-?(?:0x[0-9a-fA-F]+|\d+))\b", text, re.M)}
+    flags = {k: v for k, v in defs.items() if not k.startswith("ERR_") and k != "OK" and v > 0}
+    assert len(flags) >= 14 and "MARCH_SWEEP" in flags and "OUT_MAPPED" in flags
+    for name, value in defs.items():
+        assert hasattr(_lib, name), f"_lib.{name} is missing"
+        assert getattr(_lib, name) == value, name
+    bits = sorted(flags.values())
+    assert all(b & (b - 1) == 0 for b in bits) and len(set(bits)) == len(bits)
