@@ -2,7 +2,7 @@
 adjacent conc/flx blocks on the copy stream (default) against the last kernel storing straight into the mapped
 page-locked result (BLDFM_OUT_MAPPED + option BLDFM_B200_DIRECT_HOST).  Prints one JSON line per variant.
 
-    python scripts/direct_host_probe.py > profiles/r2_direct_host.jsonl
+    python scripts/direct_host_probe.py > profiles/r2_direct_host_and_inline_copy.jsonl  (that record also holds a since-removed variant: copies on the compute stream)
 """
 import ctypes as C
 import json

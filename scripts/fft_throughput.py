@@ -1,6 +1,6 @@
 """Back-transform kernels in the throughput regime: one batched launch of G march groups x T towers of
 config-2 size (2*G*T fields of 1536^2 padded -> 512^2), device-resident.  Prints the per-stage times.
-Used under ncu to capture k_fft_h with full grids (profiles/*_ffth_batched_ncu.txt)."""
+Used under ncu to capture k_fft_h with full grids (profiles/r1i_fft24_batched_ncu.txt, profiles/r2_fft24_batched_ncu.txt)."""
 import argparse
 import ctypes as C
 import json
