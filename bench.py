@@ -71,7 +71,7 @@ CONFIG = {"workload": WORKLOAD,
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of k_march on this workload, from the committed
 # `ncu --set full` captures under profiles/ (key: march mode, full-plane march)
 NCU_TRAFFIC = {("exact", True): 84736, ("exact", False): 90112, ("fma", False): 80640,
-               ("sweep", False): 613888}    # profiles/r2_march_sweep_ncu.txt (the per-solve table and wavenumbers; no writes)
+               ("sweep", False): 84224}     # profiles/r2_march_sweep_ncu.txt (the per-solve table and wavenumbers; no writes)
 # same for the back-transform pair in its throughput regime (128 fields): profiles/r2_fft24_batched_ncu.txt
 # (pass X 273.7 + 226.2 MB, pass Y 269.5 + 229.3 MB)
 NCU_TRAFFIC_BT = 998759168
