@@ -18,12 +18,14 @@ DEVICE = int(os.environ.get("BLDFM_B200_DEVICE", os.environ.get("LOCAL_RANK", "0
 #          the highest output level, i.e. the reference's own round-off (which is all the fast modes differ from it
 #          by) <= 1e-11 rel-L2, a decade under the 1e-10 parity bar (calibration:
 #          profiles/r2_fma_calibration.jsonl) -- and the bit-mirrored march otherwise.  The fast march is the
-#          downward sweep for one output level, the FMA-contracted upward march for several.
+#          downward sweep for one output level and the FMA-contracted shooting march for several (measured faster
+#          where every level is written out).
 # "exact": the march always mirrors the reference's operation order bit for bit.
-# "fma":   always the reference's two upward initial-value problems, FMA-contracted (46 instead of 84.5 FP64
+# "fma":   always the reference's two upward initial-value problems, FMA-contracted (46.5 instead of 84.5 FP64
 #          instructions per mode-step); differs from the reference at the reference's own round-off noise level.
-# "sweep": one output level: a single downward sweep from the radiation condition (30.5-42.5 instructions per
-#          mode-step, no cancellation: accurate to 1e-15 for every kappa); several levels: as "fma".
+# "sweep": a single downward sweep from the radiation condition (30.5-42.5 instructions per mode-step for one
+#          output level, where nothing cancels: accurate to 1e-15 for every kappa; several levels: sweep for alpha,
+#          then ONE vector upward, 2 x 30.5); "fma" where the sweep could overflow.
 MARCH_MODE = os.environ.get("BLDFM_B200_MARCH", "auto")
 # How the reference-signature solver builds its (X, Y, Z) grid arrays (solver.make_grid):
 #   "cow" (default): writable, independent arrays like the reference's np.meshgrid -- X and Y are private

@@ -561,17 +561,22 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
     // reference's own round-off (what the fast modes differ from it by) stays below 1e-11.
     int arith = (flags & BLDFM_MARCH_SWEEP) ? 2 : (flags & BLDFM_MARCH_FMA) ? 1 : 0;
     if (arith == 0 && (flags & BLDFM_MARCH_AUTO) && !analytic) {
-        arith = fft_env_int("BLDFM_B200_AUTO_SWEEP", 1) ? 2 : 1;
+        // one output level: the sweep; several: the FMA shooting march, which measured faster where every level is
+        // written out (config 3: 0.883 ms against 0.966 ms for the two-pass sweep -- that march is bound by its
+        // 4.3 GB of spectrum stores, not by FP64) -- the sweep for several levels stays an explicit choice
+        arith = (fft_env_int("BLDFM_B200_AUTO_SWEEP", 1) && lp.visited <= 1) ? 2 : 1;
         const int lvl = lp.last_level >= 0 ? lp.last_level : nz_max - 1;
         for (int gi = 0; gi < ngroups && arith; ++gi)
             if (!(march_kappa(probs[rep[(size_t)gi]], g, lvl) <= auto_kappa_limit())) arith = 0;
     }
     if (arith == 2) {
-        // the sweep serves one output level; it must be unable to overflow or to meet a singular step,
-        // otherwise the FMA-contracted upward march takes over
-        if (lp.visited > 1 || lp.snap_level < 0) arith = 1;
+        // the sweep must be unable to overflow or to meet a singular step, otherwise the FMA-contracted upward
+        // march takes over.  One output level: sweep down to the ground with the determinant product below the
+        // level; several: sweep down for alpha only (no determinants), then one vector upward (march.cuh)
+        const bool multi_levels = lp.visited > 1;
+        if (!multi_levels && lp.snap_level < 0) arith = 1;
         for (int gi = 0; gi < ngroups && arith == 2; ++gi)
-            if (!sweep_admissible(probs[rep[(size_t)gi]], g, lp.snap_level)) arith = 1;
+            if (!sweep_admissible(probs[rep[(size_t)gi]], g, multi_levels ? 0 : lp.snap_level)) arith = 1;
     }
     const bool fma_mode = arith != 0;
     pl->last_march_fma = arith;
@@ -798,7 +803,7 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         cfg.attrs = at; cfg.numAttrs = 1;                                                           \
         CUDA_TRY(cudaLaunchKernelEx(&cfg, k_march<F, M>, a));                                       \
     } while (0)
-            if (arith == 2 && !multi) LAUNCH_MARCH(2, false);
+            if (arith == 2) { if (multi) LAUNCH_MARCH(2, true); else LAUNCH_MARCH(2, false); }
             else if (fma_mode) { if (multi) LAUNCH_MARCH(1, true); else LAUNCH_MARCH(1, false); }
             else               { if (multi) LAUNCH_MARCH(0, true); else LAUNCH_MARCH(0, false); }
 #undef LAUNCH_MARCH

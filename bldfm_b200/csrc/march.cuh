@@ -13,8 +13,8 @@
 //       bit (up to the sign of exact zeros).
 //   FMA=true  (opt-in) : algebraically identical, contracted into FMAs (46 instead of 85 FP64
 //       instructions per mode-step).  Differs from the reference at the self-noise level.
-//   SWEEP (single output level): the same discrete two-point problem solved by ONE downward sweep instead of
-//       two upward initial-value problems -- see sweep_body.
+//   SWEEP: the same discrete two-point problem solved by ONE downward sweep instead of two upward
+//       initial-value problems -- see sweep_body (one output level) and sweep_multi_body (several).
 #pragma once
 
 #include "common.cuh"
@@ -395,6 +395,53 @@ __device__ __forceinline__ void sweep_body(const MarchArgs& a, const GroupDesc& 
     for (int r = 1; r < a.nlv; ++r) emit(r, 0.0, 0.0, 0.0, 0.0);
 }
 
+// Several output levels in sweep mode: the downward sweep only has to deliver alpha -- at the ground
+// v_0 = (alpha, q0) = w_0 * q0 / (w_0).q, no determinant involved -- and the solution itself is then marched
+// upward as ONE vector from (alpha, q0), emitting the requested rows on the way: 2 x 30.5 FP64 instructions per
+// mode-step against 2 x 46.5 for the FMA shooting march (which carries both auxiliary problems twice).  The
+// upward leg amplifies round-off like the reference's own combination alpha*P1 + P2 does (e^{2 kappa}), hence the
+// same kappa gate.
+template <class Coef>
+__device__ __forceinline__ void sweep_multi_body(const MarchArgs& a, const GroupDesc& gd, const Emit& emit,
+                                                 const Coef& sc, double lx, double ly, double q0r, double q0i)
+{
+    const int S = gd.S;
+    const double lx2 = lx * lx, ly2 = ly * ly;
+    double pr = 1.0, pi = 0.0, qr, qi;
+    {
+        const double are = gd.kxk * lx2 + gd.kyk * ly2;
+        const double aim = gd.c1 * lx + gd.c2 * ly;
+        double er, ei;
+        csqrt_np(are, aim, er, ei);
+        qr = gd.kz_top * er; qi = gd.kz_top * ei;
+    }
+    sc.ready();
+    if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 1] = march_now();
+    Prop P;
+#pragma unroll 4
+    for (int i = S - 1; i >= 0; --i) {
+        propagator<true>(sc[i], lx, ly, lx2, ly2, P);
+        apply_adj(P, pr, pi, qr, qi);
+    }
+    // alpha = q0 * (w_0).p / (w_0).q
+    double rr, ri, alr, ali;
+    cdiv_np(pr, pi, qr, qi, rr, ri);
+    cmul_np(q0r, q0i, rr, ri, alr, ali);
+    if (a.trace && threadIdx.x == 0) a.trace[(size_t)blockIdx.x * 4 + 2] = march_now();
+    pr = alr; pi = ali; qr = q0r; qi = q0i;
+    const int last = a.last_level < S ? a.last_level : S;
+    int rows = 0;
+    for (int i = 0; i <= last; ++i) {
+        const int row = sc.row(i, a);
+        if (row >= 0) { emit(row, pr, pi, qr, qi); ++rows; }
+        if (i < last) {
+            propagator<true>(sc[i], lx, ly, lx2, ly2, P);
+            apply<true>(P, pr, pi, qr, qi);
+        }
+    }
+    for (int r = rows; r < a.nlv; ++r) emit(r, 0.0, 0.0, 0.0, 0.0);
+}
+
 // The per-level table of the march, staged once per CTA in shared memory from the per-solve parameter buffer.
 // (Measured alternative, round 2: the table carried in the kernel's parameter space and read with
 // warp-uniform LDC inside the loop -- no H2D copy, no staging, no barrier -- is 14 % (exact) to 36 % (fma)
@@ -459,6 +506,7 @@ __device__ __forceinline__ void march_body(const MarchArgs& a, const GroupDesc& 
     };
     if (is00) { sc.ready(); mode00(); return; }
     if (ARITH == 2 && !MULTI) { sweep_body(a, gd, emit, sc, lx, ly, q0r, q0i); return; }
+    if (ARITH == 2 && MULTI) { sweep_multi_body(a, gd, emit, sc, lx, ly, q0r, q0i); return; }
 
     const double lx2 = lx * lx, ly2 = ly * ly;
     sc.ready();

@@ -56,12 +56,14 @@ extern "C" {
                                          both.  Opt-in on top (option BLDFM_B200_DIRECT_HOST = result bytes up to
                                          which): the last kernel stores straight into them, no D2H copy -- measured
                                          slower for the transform's 64-byte row segments, see DESIGN.md 6         */
-#define BLDFM_MARCH_SWEEP     0x2000 /* opt-in: one output level is solved by a single downward sweep from the radiation
-                                         condition instead of two upward initial-value problems (same discrete
-                                         solution, no cancellation, fewer flops; differs from the reference by the
-                                         reference's own round-off).  Falls back to BLDFM_MARCH_FMA for several
-                                         output levels or where the sweep could overflow                        */
-#define BLDFM_MARCH_AUTO       0x400  /* fast march (sweep, else FMA-contracted) where linear shooting is well conditioned (kappa at the
+#define BLDFM_MARCH_SWEEP     0x2000 /* opt-in: the two-point problem of every mode is solved by a single downward sweep
+                                         from the radiation condition instead of two upward initial-value problems
+                                         (same discrete solution, fewer flops; differs from the reference by the
+                                         reference's own round-off).  One output level: the sweep alone; several:
+                                         sweep for alpha, then one vector upward.  Falls back to BLDFM_MARCH_FMA
+                                         where the sweep could overflow (bldfm_sweep_admissible)                */
+#define BLDFM_MARCH_AUTO       0x400  /* fast march (sweep for one output level, FMA-contracted for several or where the sweep is not admissible)
+                                         where linear shooting is well conditioned (kappa at the
                                          highest output level <= bldfm_auto_kappa_limit() for every march of the
                                          call: predicted deviation from the reference <= 1e-11 rel-L2, SURVEY.md
                                          Appendix C), the bit-mirrored march otherwise                          */
@@ -195,7 +197,8 @@ int  bldfm_solve_batched_accumulate(bldfm_plan *plan, int32_t nprob, const bldfm
 int    bldfm_kappa(const bldfm_geometry *g, const bldfm_problem *prob, int32_t level, double *kappa);
 /* May the downward sweep (BLDFM_MARCH_SWEEP) serve this problem at output level `level`?  *ok = 1 where neither the
  * swept vector nor the determinant product can leave the binary64 range and no step can be singular (bounds at the
- * largest retained wavenumbers; pure host arithmetic).  Where it is 0 the FMA-contracted shooting march runs. */
+ * largest retained wavenumbers; pure host arithmetic).  Where it is 0 the FMA-contracted shooting march runs.
+ * (A solve with several output levels asks with level 0: its sweep needs no determinant product.) */
 int    bldfm_sweep_admissible(const bldfm_geometry *g, const bldfm_problem *prob, int32_t level, int32_t *ok);
 double bldfm_auto_kappa_limit(void);
 int    bldfm_plan_last_march_mode(const bldfm_plan *plan);

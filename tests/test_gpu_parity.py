@@ -520,23 +520,50 @@ def test_downward_sweep_equals_the_shooting_march(footprint, level, precision):
 
 
 @pytest.mark.gpu
-def test_sweep_serves_one_level_and_never_overflows():
-    """Several output levels, or a column on which the swept vector could leave the binary64 range (here: 0.06 m
-    cells, growth bound e^4000), are marched upward (FMA-contracted) even when the sweep is asked for -- and "auto"
-    takes the bit-mirrored march there because the reference itself is round-off dominated."""
+@pytest.mark.parametrize("footprint", [True, False])
+@pytest.mark.parametrize("precision", ["double", "single"])
+def test_sweep_for_several_levels_equals_the_shooting_march(footprint, precision):
+    """Several output levels in sweep mode (march.cuh::sweep_multi_body: sweep down for alpha, then ONE vector
+    upward) against the bit-mirrored shooting march, with the FMA shooting march as the yardstick; levels given
+    unsorted and with the top of the column among them."""
+    import bldfm_b200 as B
+    z, prof, q0 = _sweep_cases()
+    kw = dict(srf_flx=q0, z=z, profiles=prof, domain=(1200.0, 900.0), levels=[17, 3, 52, 32, 0], modes=(96, 64),
+              meas_pt=(310.0, 405.0), srf_bg_conc=0.0 if footprint else 0.7, footprint=footprint,
+              precision=precision)
+    prev = B.config.MARCH_MODE
+    got = {}
+    try:
+        for mode, code in (("exact", 0), ("fma", 1), ("sweep", 2)):
+            B.config.MARCH_MODE = mode
+            _, c, f = B.steady_state_transport_solver(**kw)
+            got[mode] = (np.array(c), np.array(f))
+            assert _last_march_mode(B, kw) == code
+    finally:
+        B.config.MARCH_MODE = prev
+    (c0, f0), (c1, f1), (c2, f2) = got["exact"], got["fma"], got["sweep"]
+    assert c2.shape == c0.shape == (5, 96, 128) and c2.dtype == c0.dtype
+    floor = 1e-13 if precision == "double" else 2e-7
+    for lv in range(5):
+        assert rel_l2(c2[lv], c0[lv]) <= max(floor, 4.0 * rel_l2(c1[lv], c0[lv])), lv
+        assert rel_l2(f2[lv], f0[lv]) <= max(floor, 4.0 * rel_l2(f1[lv], f0[lv])), lv
+
+
+@pytest.mark.gpu
+def test_sweep_never_overflows():
+    """A column on which the swept vector could leave the binary64 range (here: 0.06 m cells, growth bound far
+    beyond 2^512) is marched upward (FMA-contracted) even when the sweep is asked for -- and "auto" takes the
+    bit-mirrored march there because the reference itself is round-off dominated."""
     import bldfm_b200 as B
     z, prof, q0 = _sweep_cases()
     prev = B.config.MARCH_MODE
     try:
         B.config.MARCH_MODE = "sweep"
-        kw = dict(srf_flx=q0, z=z, profiles=prof, domain=(1200.0, 900.0), levels=[3, 17, 32], modes=(96, 64),
-                  footprint=False, precision="double")
-        _, c, f = B.steady_state_transport_solver(**kw)
-        assert _last_march_mode(B, kw) == 1 and c.shape == (3, 96, 128) and np.isfinite(c).all()
-        kw = dict(srf_flx=q0, z=z, profiles=prof, domain=(8.0, 6.0), levels=32, modes=(96, 64), footprint=True,
-                  precision="double")
-        _, c, f = B.steady_state_transport_solver(**kw)
-        assert _last_march_mode(B, kw) == 1
+        for levels in (32, [3, 17, 32]):
+            kw = dict(srf_flx=q0, z=z, profiles=prof, domain=(8.0, 6.0), levels=levels, modes=(96, 64),
+                      footprint=True, precision="double")
+            B.steady_state_transport_solver(**kw)
+            assert _last_march_mode(B, kw) == 1
         B.config.MARCH_MODE = "auto"
         B.steady_state_transport_solver(**kw)
         assert _last_march_mode(B, kw) == 0
