@@ -759,6 +759,14 @@ int solve_impl(bldfm_plan* pl, int nprob, const bldfm_problem* probs, const int6
         a.footprint = footprint ? 1 : 0;
         // conjugate symmetry of the spectra of a real source: march half the modes (march.cuh)
         a.herm = herm ? 1 : 0;
+        {
+            // the conjugate mirror rows are dead when the spectra go straight into the sparse radix-24/48 pass X
+            // (even sizes; the generic, full-complex and library transforms and the parity export read them)
+            const bool lib_bt = (flags & BLDFM_FFT_LIBRARY) || !pruned_fft_supported(g, spec_f32, pl->smem_optin);
+            const bool pass_x_24 = fft_env_int("BLDFM_B200_FFT24", 1) != 0 && fft24_lq(g.nfx, g.nlx, g.nx, g.px) >= 0;
+            a.skip_mirror = (herm && !sh && !spectral && !lib_bt && !(flags & BLDFM_FFT_FULL) && pass_x_24 &&
+                             g.nlx % 2 == 0 && g.nly % 2 == 0 && fft_env_int("BLDFM_B200_SKIP_MIRROR", 1) != 0) ? 1 : 0;
+        }
         a.src_pitch = src_compact ? g.nlx : g.nxe;
         a.src_nfx = src_compact ? g.nlx : g.nxe;
         a.src_nfy = src_compact ? g.nly : g.nye;

@@ -155,6 +155,7 @@ struct MarchArgs {
     int32_t out_f32;           // spectra stored as float2 (no shift applied, single)
     int32_t footprint;
     int32_t herm;              // 1: rows lie in the half-plane ky <= nly/2; conjugates are stored at (-ky,-kx)
+    int32_t skip_mirror;       // 1: ... except that nobody will read them (see below): the mirror stores are skipped
     int32_t src_pitch;         // row pitch (complex elements) of src_spec
     int32_t src_nfx, src_nfy;  // size of the forward spectrum for index wrapping
     int32_t src_ky0;           // first ky row held by src_spec (ky-slab sharding), else 0
@@ -194,7 +195,11 @@ struct Emit {
 
     __device__ __forceinline__ Emit(const MarchArgs& a_, const GroupDesc& gd_, const TowerDesc* tw_, int64_t mode_,
                                     int64_t mirror_, double lx_, double ly_)
-        : a(a_), gd(gd_), tw(tw_), mode(mode_), mirror(mirror_), lx(lx_), ly(ly_),
+        // skip_mirror: the consumer is pass X of the sparse radix-24/48 back-transform, which for a
+        // conjugate-symmetric spectrum of even size reads the rows ky <= nly/2 and, of the other rows, only the
+        // Nyquist column -- written by the extra threads as their OWN mode (fft24.cuh, "interior row"); the
+        // mirror stores would be half of this kernel's store traffic for nothing
+        : a(a_), gd(gd_), tw(tw_), mode(mode_), mirror(a_.skip_mirror ? -1 : mirror_), lx(lx_), ly(ly_),
           cs0(1.0), sn0(0.0)
     {
         if (gd.tow_count > 0 && tw[0].shift) phase(tw[0], cs0, sn0);
