@@ -68,3 +68,38 @@ def test_sparse_radix_decomposition(R0, LQ, stages):
     buf = sparse_first_stage(lambda f: x[f % N], Q, R0)
     got = inplace_dif(buf, Q, stages)
     assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+def _pass_x_reads(nlx, nly, hs):
+    """Index algebra of fft24_fetch_x (bldfm_b200/csrc/fft_herm.cuh): the elements S[row][col] that pass X of the
+    real-output back-transform reads for H[fy][f] = (S[fy][f] + conj(S[-fy][-f]))/2, fy = 0..nly/2, |f| <= nlx/2;
+    `hs`: the spectrum is conjugate-symmetric (half-plane march), interior elements are taken as H = S."""
+    hx, hy, px, py = nlx // 2, nly // 2, (nlx - 1) // 2, (nly - 1) // 2
+    reads = set()
+    for fy in range(0, hy + 1):
+        for f in range(-hx, hx + 1):
+            one = hs and -hx < f < hx and 0 < fy < hy
+            ok1 = fy <= py and -hx <= f <= px
+            ok2 = (not one) and fy <= hy and -hx <= -f <= px
+            if ok1:
+                reads.add((fy, f if f >= 0 else f + nlx))
+            if ok2:
+                reads.add(((nly - fy) if fy > 0 else 0, (nlx - f) if f > 0 else -f))
+    return reads
+
+
+def test_pass_x_never_reads_the_mirror_stores_of_an_even_conjugate_symmetric_spectrum():
+    """Why the half-plane march may skip its conjugate mirror stores (MarchArgs.skip_mirror): for even nlx, nly the
+    pass-X read set of a conjugate-symmetric spectrum lies in the rows ky <= nly/2 plus the Nyquist column of the
+    other rows (which the march writes as modes of their own, not as mirrors).  For odd sizes, or for a spectrum
+    that is not known to be symmetric, mirror-row elements are read -- there the stores stay."""
+    def mirror_reads(nlx, nly, hs):
+        return {(r, c) for (r, c) in _pass_x_reads(nlx, nly, hs) if r > nly // 2 and not (nlx % 2 == 0 and c == nlx // 2)}
+    for nlx, nly in ((8, 8), (16, 8), (8, 12), (64, 32)):
+        assert not mirror_reads(nlx, nly, True)
+        assert mirror_reads(nlx, nly, False)                       # general spectrum: both rows are combined
+        # every marched element is still read (nothing else was dropped): rows 0..nly/2, all columns
+        got = _pass_x_reads(nlx, nly, True)
+        assert {(r, c) for r in range(nly // 2 + 1) for c in range(nlx)} <= got
+    for nlx, nly in ((9, 8), (8, 9), (9, 9)):
+        assert mirror_reads(nlx, nly, True)                        # odd sizes need mirror elements
